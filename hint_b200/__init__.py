@@ -1,0 +1,13 @@
+"""hint_b200 — B200-native implementation of HINT's recursive affine coupling block (hint.py of vislearn/HINT).
+
+Importing this package loads (building in-tree if needed) the sm_100a shared library; there is no CPU path.
+"""
+from . import _lib
+from .block import (HierarchicalAffineCouplingBlock, HierarchicalAffineCouplingTree, TreePlan,
+                    linear_subnet_constructor, set_precision, get_precision)
+
+_lib.load()
+__version__ = _lib.load().hint_version().decode()
+
+__all__ = ["HierarchicalAffineCouplingBlock", "HierarchicalAffineCouplingTree", "TreePlan",
+           "linear_subnet_constructor", "set_precision", "get_precision"]

@@ -1,0 +1,93 @@
+"""ctypes binding of libhint_b200.so (the C ABI declared in include/hint_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library cannot be found or built, importing the
+product fails loudly, and compute entry points refuse non-CUDA tensors.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhint_b200.so")
+
+HINT_OK, HINT_ERR_INVALID, HINT_ERR_UNSUPPORTED, HINT_ERR_CUDA, HINT_ERR_WORKSPACE = 0, 1, 2, 3, 4
+MODE_FP32, MODE_TF32, MODE_TF32X3 = 0, 1, 2
+WS_FORWARD, WS_BACKWARD = 0, 1
+
+# every symbol include/hint_b200.h declares (tests/test_capi.py checks the header against this list)
+EXPORTS = [
+    "hint_plan_create", "hint_plan_destroy", "hint_plan_num_nodes", "hint_plan_node", "hint_plan_param_count",
+    "hint_plan_param_layout", "hint_plan_flops_per_sample", "hint_plan_tile_rows", "hint_workspace_bytes",
+    "hint_forward", "hint_backward", "hint_last_error", "hint_version",
+]
+
+
+class NodeInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("depth", "lo", "hi", "k", "cin", "h", "cout", "leaf", "parent", "upper", "lower")] + \
+               [("param_offset", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load (building in-tree first if the .so is missing or stale and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        from . import build as _build
+        if _build.is_stale():
+            _build.build()
+    except Exception as e:  # no nvcc on this machine: fall through and require the prebuilt .so
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"hint_b200: native library {LIB_PATH} is missing and could not be built ({e}). "
+                "Run `python -m hint_b200.build` (needs nvcc, sm_100a). There is no fallback path.") from e
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+    lib.hint_plan_create.restype = ctypes.c_int
+    lib.hint_plan_create.argtypes = [i32, i32, ctypes.POINTER(i32), i32, ctypes.c_double, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.hint_plan_destroy.restype = None
+    lib.hint_plan_destroy.argtypes = [vp]
+    lib.hint_plan_num_nodes.restype = i32
+    lib.hint_plan_num_nodes.argtypes = [vp]
+    lib.hint_plan_node.restype = ctypes.c_int
+    lib.hint_plan_node.argtypes = [vp, i32, ctypes.POINTER(NodeInfo)]
+    lib.hint_plan_param_count.restype = i64
+    lib.hint_plan_param_count.argtypes = [vp]
+    lib.hint_plan_param_layout.restype = ctypes.c_int
+    lib.hint_plan_param_layout.argtypes = [vp, ctypes.POINTER(i64), i64]
+    lib.hint_plan_flops_per_sample.restype = i64
+    lib.hint_plan_flops_per_sample.argtypes = [vp]
+    lib.hint_plan_tile_rows.restype = i32
+    lib.hint_plan_tile_rows.argtypes = [vp, i32]
+    lib.hint_workspace_bytes.restype = ctypes.c_size_t
+    lib.hint_workspace_bytes.argtypes = [vp, i64, i32]
+    lib.hint_forward.restype = ctypes.c_int
+    lib.hint_forward.argtypes = [vp, f32p, f32p, f32p, i64, i32, i32, f32p, f32p, vp, ctypes.c_size_t, vp]
+    lib.hint_backward.restype = ctypes.c_int
+    lib.hint_backward.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, i64, i32, f32p, f32p, f32p, f32p, vp,
+                                  ctypes.c_size_t, vp]
+    lib.hint_last_error.restype = ctypes.c_char_p
+    lib.hint_last_error.argtypes = []
+    lib.hint_version.restype = ctypes.c_char_p
+    lib.hint_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().hint_last_error().decode()
+
+
+def check(rc):
+    """Map a C status code onto the exception the reference's Python surface would raise."""
+    if rc == HINT_OK:
+        return
+    msg = last_error()
+    if rc == HINT_ERR_UNSUPPORTED:
+        raise NotImplementedError("hint_b200: " + msg)
+    if rc == HINT_ERR_INVALID:
+        raise ValueError("hint_b200: " + msg)
+    raise RuntimeError(f"hint_b200 (code {rc}): {msg}")

@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference module surface (/root/reference/hint.py:104-133).
+
+``HierarchicalAffineCouplingBlock`` keeps the FrEIA-module protocol of the reference
+(ctor kwargs, ``forward(x_list, c=[], rev=False) -> [z]``, ``jacobian()``, ``output_dims``) and its
+``state_dict`` key names (``tree.upper.s.0.weight`` ...), but holds ALL parameters of the block in one
+flat fp32 ``nn.Parameter`` in the reference's ``parameters()`` order, and runs the whole coupling tree
+in one fused CUDA kernel through the C ABI (include/hint_b200.h).  Backward is memory-free: autograd
+keeps only the block output.
+
+No CPU fallback: non-CUDA tensors raise.
+"""
+import ctypes
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "tf32x3": _lib.MODE_TF32X3, "3xtf32": _lib.MODE_TF32X3}
+_mode = os.environ.get("HINT_B200_MODE", "fp32").lower()
+
+
+def set_precision(mode: str):
+    """Select the GEMM arithmetic of all blocks without touching the configs: 'fp32' | 'tf32' | 'tf32x3'."""
+    global _mode
+    if mode.lower() not in _MODES:
+        raise ValueError(f"unknown precision mode {mode!r}; choose from {sorted(_MODES)}")
+    _mode = mode.lower()
+
+
+def get_precision() -> str:
+    return _mode
+
+
+def linear_subnet_constructor(c_in, c_out, c_internal):
+    """Shape contract of the only subnet the fused kernels implement (hint.py:10-13):
+    Linear(c_in, h) - ReLU - Linear(h, h) - ReLU - Linear(h, c_out).  Passing this function (or None) as
+    ``subnet_constructor`` selects the fused path; any other callable is rejected."""
+    return nn.Sequential(nn.Linear(c_in, c_internal), nn.ReLU(),
+                         nn.Linear(c_internal, c_internal), nn.ReLU(),
+                         nn.Linear(c_internal, c_out))
+
+
+class TreePlan:
+    """Python handle of a ``hint_plan_t`` (tree of hint.py:25-54 flattened by the C++ planner)."""
+
+    def __init__(self, d, dc, c_internal, clamp, max_splits, min_split_size, reshuffle):
+        lib = _lib.load()
+        self._lib = lib
+        ci = (ctypes.c_int32 * len(c_internal))(*[int(v) for v in c_internal])
+        handle = ctypes.c_void_p()
+        _lib.check(lib.hint_plan_create(int(d), int(dc), ci, len(c_internal), float(clamp), int(max_splits),
+                                        int(min_split_size), 1 if reshuffle else 0, ctypes.byref(handle)))
+        self._h = handle
+        self.d, self.dc, self.clamp = int(d), int(dc), float(clamp)
+        n = lib.hint_plan_num_nodes(handle)
+        self.nodes = []
+        for i in range(n):
+            info = _lib.NodeInfo()
+            _lib.check(lib.hint_plan_node(handle, i, ctypes.byref(info)))
+            self.nodes.append({f: getattr(info, f) for f, _ in _lib.NodeInfo._fields_})
+        self.n_params = int(lib.hint_plan_param_count(handle))
+        self.flops_per_sample = int(lib.hint_plan_flops_per_sample(handle))
+        offs = (ctypes.c_int64 * (n * 12))()
+        _lib.check(lib.hint_plan_param_layout(handle, offs, n * 12))
+        paths = {}
+        for i, nd in enumerate(self.nodes):
+            if nd["parent"] < 0:
+                paths[i] = "tree"
+            else:
+                par = self.nodes[nd["parent"]]
+                paths[i] = paths[nd["parent"]] + (".upper" if par["upper"] == i else ".lower")
+        self.paths = paths
+        # (name, offset, shape) in the reference's parameters() order
+        self.entries = []
+        for i, nd in enumerate(self.nodes):
+            dims = [(nd["h"], nd["cin"]), (nd["h"], nd["h"]), (nd["cout"], nd["h"])]
+            for net, netname in enumerate("st"):
+                for layer, (o, k) in enumerate(dims):
+                    base = i * 12 + net * 6 + layer * 2
+                    self.entries.append((f"{paths[i]}.{netname}.{2 * layer}.weight", int(offs[base]), (o, k)))
+                    self.entries.append((f"{paths[i]}.{netname}.{2 * layer}.bias", int(offs[base + 1]), (o,)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.hint_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tile_rows(self, which=_lib.WS_FORWARD):
+        return int(self._lib.hint_plan_tile_rows(self._h, which))
+
+    # -- launches ------------------------------------------------------------------------------
+    @staticmethod
+    def _check(t, name, shape=None):
+        if t is None:
+            return
+        if not t.is_cuda:
+            raise RuntimeError(f"hint_b200: {name} must be a CUDA tensor (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"hint_b200: {name} must be float32, got {t.dtype}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"hint_b200: {name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+
+    def forward(self, x, c, flat, rev=False, mode=None):
+        """z, logdet = f(x; c) (rev=False) or f^-1(x; c) (rev=True).  hint.py:62-101."""
+        B = x.shape[0]
+        self._check(x, "x", (B, self.d))
+        self._check(flat, "params", (self.n_params,))
+        if self.dc:
+            if c is None:
+                raise ValueError("hint_b200: block was built with dims_c but no condition was passed")
+            self._check(c, "c", (B, self.dc))
+            c = c.contiguous()
+        x = x.contiguous()
+        flat = flat.contiguous()
+        with torch.cuda.device(x.device):
+            z = torch.empty_like(x)
+            J = torch.empty(B, dtype=torch.float32, device=x.device)
+            nbytes = self._lib.hint_workspace_bytes(self._h, B, _lib.WS_FORWARD)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.check(self._lib.hint_forward(self._h, x.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(), B,
+                                              1 if rev else 0, _MODES[mode or _mode], z.data_ptr(), J.data_ptr(),
+                                              ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+        return z, J
+
+    def backward(self, z, c, flat, dz, dJ, mode=None, want_xrec=False, want_dc=True):
+        """Gradients of the rev=False direction from the block OUTPUT z (memory-free backward)."""
+        B = z.shape[0]
+        self._check(z, "z", (B, self.d))
+        self._check(dz, "dz", (B, self.d))
+        self._check(dJ, "dlogdet", (B,))
+        self._check(flat, "params", (self.n_params,))
+        if self.dc:
+            self._check(c, "c", (B, self.dc))
+            c = c.contiguous()
+        z, dz, dJ, flat = z.contiguous(), dz.contiguous(), dJ.contiguous(), flat.contiguous()
+        with torch.cuda.device(z.device):
+            dx = torch.empty_like(z)
+            dc = torch.empty(B, self.dc, dtype=torch.float32, device=z.device) if (self.dc and want_dc) else None
+            xrec = torch.empty_like(z) if want_xrec else None
+            dflat = torch.empty_like(flat)
+            nbytes = self._lib.hint_workspace_bytes(self._h, B, _lib.WS_BACKWARD)
+            if nbytes == 0:
+                _lib.check(_lib.HINT_ERR_CUDA)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+            _lib.check(self._lib.hint_backward(self._h, z.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(),
+                                               dz.data_ptr(), dJ.data_ptr(), B, _MODES[mode or _mode],
+                                               xrec.data_ptr() if want_xrec else None, dx.data_ptr(),
+                                               dc.data_ptr() if dc is not None else None, dflat.data_ptr(),
+                                               ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+        return dx, dc, dflat, xrec
+
+
+class _CouplingFn(torch.autograd.Function):
+    """z, logdet = block(x, c).  Saves only the OUTPUT z (+ c, params); backward re-derives the rest."""
+
+    @staticmethod
+    def forward(ctx, x, c, flat, plan, rev):
+        z, J = plan.forward(x, c, flat, rev)
+        ctx.plan, ctx.rev = plan, rev
+        ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat)
+        return z, J
+
+    @staticmethod
+    def backward(ctx, dz, dJ):
+        if ctx.rev:
+            raise NotImplementedError("hint_b200: gradients through the rev=True direction are not implemented yet")
+        z, c, flat = ctx.saved_tensors
+        plan = ctx.plan
+        if dz is None:
+            dz = torch.zeros_like(z)
+        if dJ is None:
+            dJ = torch.zeros(z.shape[0], dtype=z.dtype, device=z.device)
+        dx, dc, dflat, _ = plan.backward(z, c if plan.dc else None, flat, dz, dJ, want_dc=ctx.needs_input_grad[1])
+        return (dx if ctx.needs_input_grad[0] else None, dc if ctx.needs_input_grad[1] else None,
+                dflat if ctx.needs_input_grad[2] else None, None, None)
+
+
+class _LinearView:
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class _SubnetView:
+    """Read/write views of one subnet's tensors with the reference's indices: net[0], net[2], net[4]."""
+
+    def __init__(self, layers):
+        self._layers = layers
+
+    def __getitem__(self, i):
+        return self._layers[i]
+
+
+class HierarchicalAffineCouplingTree:
+    """Structural view of one tree node (reference: hint.py:21-101).  Not an nn.Module: it owns no storage;
+    ``.s[0].weight`` etc. are views into the owning block's flat parameter."""
+
+    def __init__(self, block, idx):
+        self._block, self._idx = block, idx
+        nd = block.plan.nodes[idx]
+        self.data_shape = (nd["hi"] - nd["lo"],)
+        self.clamp = block.plan.clamp
+        self.split_idx = nd["k"]
+        self.conditional = block.plan.dc > 0
+        self.leaf = bool(nd["leaf"])
+        self.perm = None
+
+    def _net(self, netname):
+        b = self._block
+        path = b.plan.paths[self._idx]
+        views = b.named_views()
+        return _SubnetView({2 * l: _LinearView(views[f"{path}.{netname}.{2 * l}.weight"], views[f"{path}.{netname}.{2 * l}.bias"])
+                            for l in range(3)})
+
+    @property
+    def s(self):
+        return self._net("s")
+
+    @property
+    def t(self):
+        return self._net("t")
+
+    @property
+    def upper(self):
+        nd = self._block.plan.nodes[self._idx]
+        return None if nd["leaf"] else HierarchicalAffineCouplingTree(self._block, nd["upper"])
+
+    @property
+    def lower(self):
+        nd = self._block.plan.nodes[self._idx]
+        return None if nd["leaf"] else HierarchicalAffineCouplingTree(self._block, nd["lower"])
+
+
+class HierarchicalAffineCouplingBlock(nn.Module):
+    """Drop-in for hint.py:104-133 (same ctor signature, forward/jacobian/output_dims protocol)."""
+
+    def __init__(self, dims_in, dims_c=[], conv=False, subnet_constructor=None, c_internal=[], clamp=4.,
+                 max_splits=-1, min_split_size=2, reshuffle=False):
+        super().__init__()
+        assert all([tuple(dims_c[i][1:]) == tuple(dims_in[0][1:]) for i in range(len(dims_c))]), \
+            "Dimensions of input and one or more conditions don't agree."
+        if conv or len(dims_in[0]) != 1:
+            raise NotImplementedError("hint_b200: conv=True / image-shaped inputs are outside the fused path "
+                                      "(no reference config uses them)")
+        if subnet_constructor is not None and subnet_constructor is not linear_subnet_constructor:
+            raise NotImplementedError("hint_b200: only the default 3-layer ReLU MLP subnet (hint.py:10-13) is fused; "
+                                      "custom subnet_constructor is not supported and there is no fallback")
+        d = int(dims_in[0][0])
+        dc = int(sum(dims_c[i][0] for i in range(len(dims_c))))
+        self.dims_c = [tuple(t) for t in dims_c]
+        self.plan = TreePlan(d, dc, list(c_internal), clamp, max_splits, min_split_size, reshuffle)
+        self.flat = nn.Parameter(torch.empty(self.plan.n_params, dtype=torch.float32))
+        self.reset_parameters()
+        self.jac = None
+
+    # -- parameters ------------------------------------------------------------------------------
+    def reset_parameters(self):
+        """nn.Linear's default init per layer (what the reference gets from torch): U(-1/sqrt(fan_in), +)."""
+        with torch.no_grad():
+            fan_in = 0
+            for name, off, shape in self.plan.entries:
+                if len(shape) == 2:  # a bias uses the bound of the weight that precedes it
+                    fan_in = shape[1]
+                bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+                self.flat.data[off:off + math.prod(shape)].uniform_(-bound, bound)
+
+    def named_views(self):
+        """{reference state_dict name: view into the flat parameter}."""
+        out = {}
+        data = self.flat.data
+        for name, off, shape in self.plan.entries:
+            n = 1
+            for s in shape:
+                n *= s
+            out[name] = data[off:off + n].view(*shape)
+        return out
+
+    @property
+    def tree(self):
+        return HierarchicalAffineCouplingTree(self, 0)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for name, v in self.named_views().items():
+            destination[prefix + name] = v if keep_vars else v.detach().clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        views = self.named_views()
+        seen = set()
+        for name, v in views.items():
+            key = prefix + name
+            if key not in state_dict:
+                missing_keys.append(key)
+                continue
+            seen.add(key)
+            src = state_dict[key]
+            if tuple(src.shape) != tuple(v.shape):
+                error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(src.shape)} from "
+                                  f"checkpoint, the shape in current model is {tuple(v.shape)}.")
+                continue
+            with torch.no_grad():
+                v.copy_(src)
+        if strict:
+            for key in state_dict.keys():
+                if key.startswith(prefix) and key not in seen:
+                    unexpected_keys.append(key)
+
+    # -- FrEIA module protocol -------------------------------------------------------------------
+    def forward(self, x, c=[], rev=False):
+        x0 = x[0]
+        cc = None
+        if self.plan.dc:
+            cc = c[0] if len(c) == 1 else torch.cat(list(c), dim=1)
+        if torch.is_grad_enabled() and (x0.requires_grad or self.flat.requires_grad or (cc is not None and cc.requires_grad)):
+            z, self.jac = _CouplingFn.apply(x0, cc, self.flat, self.plan, bool(rev))
+        else:
+            z, self.jac = self.plan.forward(x0, cc, self.flat.detach(), bool(rev))
+        return [z]
+
+    def jacobian(self, x, c=[], rev=False):
+        return self.jac
+
+    def output_dims(self, input_dims):
+        assert len(input_dims) == 1, "Can only use one input."
+        return input_dims
+
+    def extra_repr(self):
+        p = self.plan
+        return (f"d={p.d}, dc={p.dc}, nodes={len(p.nodes)}, params={p.n_params}, clamp={p.clamp}, "
+                f"tile_rows(fwd/bwd)={p.tile_rows(0)}/{p.tile_rows(1)}, mode={_mode}")

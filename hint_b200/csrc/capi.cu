@@ -1,0 +1,311 @@
+// C ABI of hint_b200 (see include/hint_b200.h).  Host glue only: validates arguments, uploads the
+// plan's descriptor tables once per device, and launches the kernels on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "plan.h"
+#include "simt_kernels.cuh"
+
+using namespace hint;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(HINT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+struct DevSchedule {
+    CG* cgs = nullptr;
+    Ep* eps = nullptr;
+    DwJob* dwjobs = nullptr;
+    Stage* stages = nullptr;
+    int max_ctas = 0;  // SMs x occupancy
+};
+
+struct DevPlan {
+    DevSchedule fwd, bwd;
+    int* pack_src = nullptr;
+    int* unpack_src = nullptr;
+    int num_sms = 0;
+};
+
+}  // namespace
+
+struct hint_plan {
+    Plan p;
+    std::mutex mu;
+    std::map<int, DevPlan> dev;  // per CUDA device ordinal
+};
+
+namespace {
+
+template <typename T>
+cudaError_t upload(T** dst, const std::vector<T>& v) {
+    *dst = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+template <int TM>
+cudaError_t setup_kernels(const Schedule& s, bool bwd, int num_sms, int* max_ctas) {
+    const void* fn = bwd ? (const void*)hint_bwd_fp32_kernel<TM> : (const void*)hint_fwd_fp32_kernel<TM>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, s.smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    *max_ctas = occ * num_sms;
+    return cudaSuccess;
+}
+
+cudaError_t setup_schedule(const Schedule& s, bool bwd, int num_sms, DevSchedule& ds) {
+    cudaError_t e;
+    if ((e = upload(&ds.cgs, s.cgs)) != cudaSuccess) return e;
+    if ((e = upload(&ds.eps, s.eps)) != cudaSuccess) return e;
+    if ((e = upload(&ds.dwjobs, s.dwjobs)) != cudaSuccess) return e;
+    if ((e = upload(&ds.stages, s.stages)) != cudaSuccess) return e;
+    switch (s.TM) {
+        case 128: return setup_kernels<128>(s, bwd, num_sms, &ds.max_ctas);
+        case 64: return setup_kernels<64>(s, bwd, num_sms, &ds.max_ctas);
+        case 32: return setup_kernels<32>(s, bwd, num_sms, &ds.max_ctas);
+        case 16: return setup_kernels<16>(s, bwd, num_sms, &ds.max_ctas);
+        case 8: return setup_kernels<8>(s, bwd, num_sms, &ds.max_ctas);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Device-side tables for the current device (created on first use).
+int get_dev(hint_plan* hp, DevPlan** out) {
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(hp->mu);
+    auto it = hp->dev.find(dev);
+    if (it != hp->dev.end()) { *out = &it->second; return HINT_OK; }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(HINT_ERR_UNSUPPORTED, "hint_b200 kernels are built for sm_100a only; device is sm_" +
+                                              std::to_string(prop.major) + std::to_string(prop.minor));
+    DevPlan d;
+    d.num_sms = prop.multiProcessorCount;
+    CUDA_TRY(setup_schedule(hp->p.fwd, false, d.num_sms, d.fwd));
+    CUDA_TRY(setup_schedule(hp->p.bwd, true, d.num_sms, d.bwd));
+    CUDA_TRY(upload(&d.pack_src, hp->p.pack_src));
+    CUDA_TRY(upload(&d.unpack_src, hp->p.unpack_src));
+    auto res = hp->dev.emplace(dev, d);
+    *out = &res.first->second;
+    return HINT_OK;
+}
+
+DevTables make_tables(const Plan& p, const Schedule& s, const DevSchedule& ds) {
+    DevTables t;
+    t.cgs = ds.cgs; t.eps = ds.eps; t.dwjobs = ds.dwjobs; t.stages = ds.stages;
+    t.nstages = (int)s.stages.size();
+    t.d = p.d; t.dc = p.dc;
+    t.col_x = s.col_x; t.col_d = s.col_d; t.col_one = s.col_one; t.col_zero = s.col_zero;
+    t.raw_off = s.raw_off;
+    t.alpha = p.alpha;
+    return t;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int pack_weights(const hint_plan* hp, const DevPlan& d, const float* params, float* packed, cudaStream_t st) {
+    const long long n = hp->p.n_packed;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
+    hint_pack_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, n);
+    CUDA_TRY(cudaGetLastError());
+    return HINT_OK;
+}
+
+long long bwd_ctas(const Plan& p, const DevPlan& d, long long B) {
+    const long long ntiles = (B + p.bwd.TM - 1) / p.bwd.TM;
+    return std::min<long long>(ntiles, d.bwd.max_ctas);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hint_last_error(void) { return g_err.c_str(); }
+const char* hint_version(void) { return "hint_b200 0.1 sm_100a"; }
+
+int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n_internal, double clamp,
+                     int32_t max_splits, int32_t min_split_size, int32_t reshuffle, hint_plan_t** out) {
+    if (!out) return fail(HINT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    hint_plan* hp = new hint_plan();
+    int code = HINT_OK;
+    std::string err = build_plan(hp->p, d, dc, c_internal, n_internal, clamp, max_splits, min_split_size, reshuffle, &code);
+    if (!err.empty()) {
+        delete hp;
+        return fail(code, err);
+    }
+    *out = hp;
+    return HINT_OK;
+}
+
+void hint_plan_destroy(hint_plan_t* hp) {
+    if (!hp) return;
+    for (auto& kv : hp->dev) {
+        DevPlan& d = kv.second;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) break;
+        if (cudaSetDevice(kv.first) != cudaSuccess) continue;
+        for (DevSchedule* s : {&d.fwd, &d.bwd}) {
+            cudaFree(s->cgs); cudaFree(s->eps); cudaFree(s->dwjobs); cudaFree(s->stages);
+        }
+        cudaFree(d.pack_src); cudaFree(d.unpack_src);
+        cudaSetDevice(cur);
+    }
+    delete hp;
+}
+
+int32_t hint_plan_num_nodes(const hint_plan_t* hp) { return hp ? (int32_t)hp->p.nodes.size() : 0; }
+
+int hint_plan_node(const hint_plan_t* hp, int32_t idx, hint_node_info_t* out) {
+    if (!hp || !out || idx < 0 || idx >= (int32_t)hp->p.nodes.size()) return fail(HINT_ERR_INVALID, "bad node index");
+    *out = hp->p.nodes[idx];
+    return HINT_OK;
+}
+
+int64_t hint_plan_param_count(const hint_plan_t* hp) { return hp ? hp->p.n_params : 0; }
+
+int hint_plan_param_layout(const hint_plan_t* hp, int64_t* offsets, int64_t n_offsets) {
+    if (!hp || !offsets || n_offsets != (int64_t)hp->p.param_offsets.size())
+        return fail(HINT_ERR_INVALID, "offsets must hold num_nodes*12 entries");
+    std::memcpy(offsets, hp->p.param_offsets.data(), sizeof(int64_t) * (size_t)n_offsets);
+    return HINT_OK;
+}
+
+int64_t hint_plan_flops_per_sample(const hint_plan_t* hp) { return hp ? hp->p.flops : 0; }
+
+int32_t hint_plan_tile_rows(const hint_plan_t* hp, int32_t which) {
+    if (!hp) return 0;
+    return which == HINT_WS_BACKWARD ? hp->p.bwd.TM : hp->p.fwd.TM;
+}
+
+size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
+    hint_plan* hp = const_cast<hint_plan*>(hp_c);
+    if (!hp || B < 0) { fail(HINT_ERR_INVALID, "bad plan or batch"); return 0; }
+    size_t bytes = align256((size_t)hp->p.n_packed * 4);
+    if (which == HINT_WS_BACKWARD) {
+        DevPlan* d = nullptr;
+        if (get_dev(hp, &d) != HINT_OK) return 0;
+        bytes += align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
+    }
+    return bytes + 256;
+}
+
+static int check_common(const hint_plan* hp, const float* x, const float* c, const float* params, int64_t B, int32_t mode) {
+    if (!hp) return fail(HINT_ERR_INVALID, "plan is NULL");
+    if (B < 0) return fail(HINT_ERR_INVALID, "negative batch");
+    if (mode != HINT_MODE_FP32)
+        return fail(HINT_ERR_UNSUPPORTED, "only HINT_MODE_FP32 is built in this version (tcgen05 TF32 modes pending)");
+    if (B > 0 && (!x || !params)) return fail(HINT_ERR_INVALID, "NULL input pointer");
+    if (B > 0 && hp->p.dc > 0 && !c) return fail(HINT_ERR_INVALID, "plan has a condition input but c is NULL");
+    if (!aligned16(x) || !aligned16(c) || !aligned16(params)) return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
+    return HINT_OK;
+}
+
+int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const float* params, int64_t B, int32_t rev,
+                 int32_t mode, float* z, float* logdet, void* workspace, size_t workspace_bytes, void* stream) {
+    hint_plan* hp = const_cast<hint_plan*>(hp_c);
+    int rc = check_common(hp, x, c, params, B, mode);
+    if (rc != HINT_OK) return rc;
+    if (B == 0) return HINT_OK;
+    if (!z || !logdet) return fail(HINT_ERR_INVALID, "NULL output pointer");
+    if (!aligned16(z) || !aligned16(workspace)) return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (z == x) return fail(HINT_ERR_INVALID, "z must not alias x");
+    DevPlan* d = nullptr;
+    if ((rc = get_dev(hp, &d)) != HINT_OK) return rc;
+    if (!workspace || workspace_bytes < hint_workspace_bytes(hp, B, HINT_WS_FORWARD))
+        return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* packed = reinterpret_cast<float*>(workspace);
+    if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
+    const Schedule& s = hp->p.fwd;
+    const DevTables T = make_tables(hp->p, s, d->fwd);
+    const long long ntiles = (B + s.TM - 1) / s.TM;
+    const int grid = (int)std::min<long long>(ntiles, d->fwd.max_ctas);
+#define LAUNCH_FWD(TMV)                                                                                   \
+    case TMV:                                                                                             \
+        hint_fwd_fp32_kernel<TMV><<<grid, kThreads, s.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B, rev ? 1 : 0); \
+        break;
+    switch (s.TM) {
+        LAUNCH_FWD(128) LAUNCH_FWD(64) LAUNCH_FWD(32) LAUNCH_FWD(16) LAUNCH_FWD(8)
+        default: return fail(HINT_ERR_INVALID, "bad tile size");
+    }
+#undef LAUNCH_FWD
+    CUDA_TRY(cudaGetLastError());
+    return HINT_OK;
+}
+
+int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const float* params, const float* dz,
+                  const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    hint_plan* hp = const_cast<hint_plan*>(hp_c);
+    int rc = check_common(hp, z, c, params, B, mode);
+    if (rc != HINT_OK) return rc;
+    if (!dparams) return fail(HINT_ERR_INVALID, "dparams is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        CUDA_TRY(cudaMemsetAsync(dparams, 0, (size_t)hp->p.n_params * 4, st));
+        return HINT_OK;
+    }
+    if (!dz || !dlogdet || !dx) return fail(HINT_ERR_INVALID, "NULL gradient pointer");
+    if (!aligned16(dz) || !aligned16(dx) || !aligned16(dc) || !aligned16(x_rec) || !aligned16(workspace))
+        return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
+    DevPlan* d = nullptr;
+    if ((rc = get_dev(hp, &d)) != HINT_OK) return rc;
+    if (!workspace || workspace_bytes < hint_workspace_bytes(hp, B, HINT_WS_BACKWARD))
+        return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    float* packed = reinterpret_cast<float*>(workspace);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->p.n_packed * 4));
+    if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
+    const Schedule& s = hp->p.bwd;
+    const DevTables T = make_tables(hp->p, s, d->bwd);
+    const int grid = (int)bwd_ctas(hp->p, *d, B);
+#define LAUNCH_BWD(TMV)                                                                                        \
+    case TMV:                                                                                                  \
+        hint_bwd_fp32_kernel<TMV><<<grid, kThreads, s.smem_bytes, st>>>(T, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, \
+                                                                         (long long)hp->p.n_partial, (long long)B); \
+        break;
+    switch (s.TM) {
+        LAUNCH_BWD(128) LAUNCH_BWD(64) LAUNCH_BWD(32) LAUNCH_BWD(16) LAUNCH_BWD(8)
+        default: return fail(HINT_ERR_INVALID, "bad tile size");
+    }
+#undef LAUNCH_BWD
+    CUDA_TRY(cudaGetLastError());
+    {
+        const long long n = hp->p.n_params;
+        const int threads = 256;
+        const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->unpack_src, partials, grid, (long long)hp->p.n_partial, dparams, n);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return HINT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+/*
+ * hint_b200 — C ABI of the B200-native HINT coupling-block hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the
+ * hot path is the pure-Python module /root/reference/hint.py.  Each entry point below replaces the
+ * part of that file named in its comment; the Python host (hint_b200/block.py) binds these symbols
+ * with ctypes and keeps hint.py's nn.Module surface on top of them.
+ *
+ * Conventions
+ *   - All tensors are dense fp32, row-major, device pointers on the CURRENT CUDA device, base
+ *     pointers 16-byte aligned.  x/z/dz/dx are [B, d]; c/dc are [B, dc] (all conditions of
+ *     hint.py:76 concatenated in list order; NULL when dc == 0); logdet/dlogdet are [B].
+ *   - `params` / `dparams` are flat vectors in the reference's `parameters()` order: pre-order over
+ *     tree nodes, per node s.0.weight, s.0.bias, s.2.weight, s.2.bias, s.4.weight, s.4.bias, then
+ *     t.* (hint.py:44-45,49-52; nn.Linear weights are [out, in]).  hint_plan_param_layout() gives
+ *     the offsets, so a host can expose reference-named views of one flat buffer.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync inside.
+ *   - Return value: HINT_OK or an error code; hint_last_error() returns a thread-local message.
+ *   - There is no CPU path: calling a compute entry point without a usable sm_100 device fails.
+ */
+#ifndef HINT_B200_H
+#define HINT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HINT_OK 0
+#define HINT_ERR_INVALID 1      /* bad shape / NULL pointer / misaligned pointer               */
+#define HINT_ERR_UNSUPPORTED 2  /* option outside the fused path (conv, custom subnet, reshuffle) */
+#define HINT_ERR_CUDA 3         /* CUDA runtime error (message carries cudaGetErrorString)      */
+#define HINT_ERR_WORKSPACE 4    /* workspace smaller than hint_workspace_bytes()                */
+
+/* arithmetic mode of the subnet GEMMs (accumulation is always fp32) */
+#define HINT_MODE_FP32 0        /* CUDA-core FFMA, bit-for-bit fp32 products                    */
+#define HINT_MODE_TF32 1        /* tcgen05 kind::tf32, operands rounded to 10-bit mantissa      */
+#define HINT_MODE_TF32X3 2      /* tcgen05 3xTF32 split (big*big + big*small + small*big)       */
+
+/* which workspace hint_workspace_bytes() sizes */
+#define HINT_WS_FORWARD 0
+#define HINT_WS_BACKWARD 1
+
+typedef struct hint_plan hint_plan_t;
+
+/* One tree node of hint.py:25-54, flattened.  Nodes are numbered in pre-order (root 0, then the
+ * whole upper subtree, then the lower subtree); every node owns the contiguous input columns
+ * [lo, hi).  upper half = [lo, lo+k), lower half = [lo+k, hi)  (hint.py:41,68). */
+typedef struct hint_node_info {
+    int32_t depth, lo, hi, k;
+    int32_t cin;    /* k + dc             (hint.py:44) */
+    int32_t h;      /* hidden width       (hint.py:31-34,50) */
+    int32_t cout;   /* (hi - lo) - k      (hint.py:44) */
+    int32_t leaf;   /* hint.py:47,54 */
+    int32_t parent, upper, lower;
+    int64_t param_offset; /* offset of this node's s.0.weight in the flat parameter vector */
+} hint_node_info_t;
+
+/* --- plan: replaces HierarchicalAffineCouplingTree.__init__ (hint.py:25-54) and the ctor argument
+ * checks of HierarchicalAffineCouplingBlock.__init__ (hint.py:108-122).
+ * c_internal/n_internal: hidden widths per depth (empty -> [d], last entry repeats).
+ * reshuffle != 0 is rejected with HINT_ERR_UNSUPPORTED (FrEIA HouseholderPerm, parity unpinned). */
+int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n_internal, double clamp,
+                     int32_t max_splits, int32_t min_split_size, int32_t reshuffle, hint_plan_t** out);
+void hint_plan_destroy(hint_plan_t* plan);
+
+int32_t hint_plan_num_nodes(const hint_plan_t* plan);
+int hint_plan_node(const hint_plan_t* plan, int32_t idx, hint_node_info_t* out);
+int64_t hint_plan_param_count(const hint_plan_t* plan);
+/* offsets[n*12 + net*6 + layer*2 + kind]: net 0=s 1=t, layer 0..2, kind 0=weight 1=bias */
+int hint_plan_param_layout(const hint_plan_t* plan, int64_t* offsets, int64_t n_offsets);
+/* algorithmic forward FLOPs per sample: sum_nodes 2*2*(cin*h + h*h + h*cout)   */
+int64_t hint_plan_flops_per_sample(const hint_plan_t* plan);
+/* samples per CTA tile chosen for the forward / backward schedule (for reporting) */
+int32_t hint_plan_tile_rows(const hint_plan_t* plan, int32_t which);
+
+size_t hint_workspace_bytes(const hint_plan_t* plan, int64_t B, int32_t which);
+
+/* --- forward / inverse transport + log|det J|: replaces HierarchicalAffineCouplingTree.forward
+ * (hint.py:62-101) as called by HierarchicalAffineCouplingBlock.forward (hint.py:124-126).
+ * rev == 0: z = f(x; c), logdet = +sum log e(s).   rev != 0: z = f^-1(x; c), logdet = -sum log e(s).
+ * x is not modified; z must not alias x. */
+int hint_forward(const hint_plan_t* plan, const float* x, const float* c, const float* params, int64_t B,
+                 int32_t rev, int32_t mode, float* z, float* logdet, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* --- backward of the rev == 0 direction: replaces the autograd tape the reference builds over
+ * hint.py:62-101 (triggered at train_unconditional.py:137).  Memory-free: takes the block OUTPUT z
+ * (and c), re-derives every node's input by running the inverse sweep inside the kernel, and emits
+ * dx [B,d], dc [B,dc] (NULL allowed), dparams [param_count] (overwritten, not accumulated) for
+ * upstream gradients dz [B,d] and dlogdet [B].  x_rec (optional, may be NULL) receives the
+ * reconstructed block input f^-1(z). */
+int hint_backward(const hint_plan_t* plan, const float* z, const float* c, const float* params,
+                  const float* dz, const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx,
+                  float* dc, float* dparams, void* workspace, size_t workspace_bytes, void* stream);
+
+const char* hint_last_error(void);
+/* "hint_b200 <version> sm_100a" — lets the host check it loaded the in-tree build */
+const char* hint_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HINT_B200_H */

@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol the header
+declares, and its planner (tree / parameter layout, integer work -> bit-exact) agrees with the oracle and with
+the reference's state_dict layout stored in the golden fixtures.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, plan_kwargs
+from oracle import hint_oracle as O
+
+import hint_b200
+from hint_b200 import _lib, HierarchicalAffineCouplingBlock, TreePlan
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hint_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(hint_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in _lib.load().hint_version()
+
+
+@pytest.mark.parametrize("kat", O.PARAM_COUNT_KATS, ids=lambda k: k["name"])
+def test_planner_matches_oracle_and_param_kats(kat):
+    plan = TreePlan(kat["d"], kat["dc"], kat["c_internal"], 4.0, kat["max_splits"], 2, False)
+    assert plan.n_params == kat["per_block"]
+    oplan = O.build_plan(kat["d"], kat["dc"], kat["c_internal"], kat["max_splits"])
+    assert len(plan.nodes) == len(oplan)
+    for a, b in zip(plan.nodes, oplan):
+        for f in ("depth", "lo", "hi", "k", "cin", "h", "cout", "parent", "upper", "lower"):
+            assert a[f] == getattr(b, f), (f, a, b)
+        assert bool(a["leaf"]) == b.leaf
+    assert plan.flops_per_sample == O.flops_per_sample(oplan)
+    mine = [(n, o, tuple(s)) for n, o, s in plan.entries]
+    ref = [(e.name, e.offset, tuple(e.shape)) for e in O.param_entries(oplan)]
+    assert mine == ref
+
+
+def test_state_dict_layout_matches_reference(golden):
+    meta = golden["meta"]
+    pk = plan_kwargs(meta)
+    blk = HierarchicalAffineCouplingBlock([(meta["d"],)], dims_c=[tuple(t) for t in meta["dims_c"]], **meta["kwargs"])
+    sd = blk.state_dict()
+    assert [(k, list(v.shape)) for k, v in sd.items()] == [(k, s) for k, s in meta["state_dict"]]
+    assert blk.plan.n_params == golden["params"].size
+    # loading a reference-layout state_dict fills the flat parameter in parameters() order
+    ref_sd, off = {}, 0
+    for k, s in meta["state_dict"]:
+        n = int(np.prod(s))
+        ref_sd[k] = torch.from_numpy(golden["params"][off:off + n].reshape(s).copy())
+        off += n
+    blk.load_state_dict(ref_sd)
+    assert np.array_equal(blk.flat.detach().numpy(), golden["params"])
+    assert [p.requires_grad for p in blk.parameters()] == [True]
+    t = blk.tree
+    assert t.s[0].weight.shape == tuple(meta["state_dict"][0][1])
+    with pytest.raises(RuntimeError):
+        blk.load_state_dict({k: v for k, v in list(ref_sd.items())[1:]})
+
+
+def test_ctor_errors_mirror_reference_surface():
+    with pytest.raises(AssertionError):
+        HierarchicalAffineCouplingBlock([(8, 4, 4)], dims_c=[(2, 3, 3)])
+    with pytest.raises(NotImplementedError):
+        HierarchicalAffineCouplingBlock([(8,)], conv=True)
+    with pytest.raises(NotImplementedError):
+        HierarchicalAffineCouplingBlock([(8,)], subnet_constructor=lambda a, b, c: None)
+    with pytest.raises(NotImplementedError):
+        HierarchicalAffineCouplingBlock([(8,)], reshuffle=True)
+    with pytest.raises(ValueError):
+        HierarchicalAffineCouplingBlock([(1,)])
+    blk = HierarchicalAffineCouplingBlock([(8,)], subnet_constructor=hint_b200.linear_subnet_constructor)
+    assert blk.output_dims([(8,)]) == [(8,)]
+    with pytest.raises(AssertionError):
+        blk.output_dims([(8,), (8,)])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk([torch.randn(3, 8)])   # no CPU fallback
+
+
+def test_default_init_distribution_matches_nn_linear():
+    torch.manual_seed(0)
+    blk = HierarchicalAffineCouplingBlock([(100,)], c_internal=[64, 32])
+    v = blk.named_views()
+    w = v["tree.s.2.weight"]
+    bound = 1 / np.sqrt(64)
+    assert w.abs().max() <= bound and w.abs().max() > 0.9 * bound
+    assert abs(float(w.std()) - bound / np.sqrt(3)) < 0.05 * bound
+
+
+def test_import_shim_names():
+    import hint
+    assert hint.HierarchicalAffineCouplingBlock is HierarchicalAffineCouplingBlock
+    assert callable(hint.linear_subnet_constructor)

@@ -1,0 +1,191 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the reference-facing module
+(HierarchicalAffineCouplingBlock) and therefore through the C ABI; the checker is the golden vectors of the real
+reference module and the CPU oracle on identical seeded inputs.
+
+Tolerances (fp32 mode; north_star: 1e-5 relative for z, x-reconstruction and log-det):
+  z, xinv, logdet : 1e-5 * max(1, max|ref|)  against the reference's fp64 outputs
+  gradients       : 2e-4 relative (max-norm) against fp64 reference gradients (memory-free backward reconstructs
+                    the block input from its output in fp32, which adds ~1e-6 relative per inversion)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import plan_kwargs
+from oracle import hint_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+GTOL = 2e-4
+
+
+def _blk(meta):
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    return HierarchicalAffineCouplingBlock([(meta["d"],)], dims_c=[tuple(t) for t in meta["dims_c"]], **meta["kwargs"])
+
+
+def _split_c(c, dims_c, dev):
+    if c is None:
+        return []
+    out, o = [], 0
+    for t in dims_c:
+        out.append(torch.from_numpy(c[:, o:o + t[0]].copy()).to(dev))
+        o += t[0]
+    return out
+
+
+def _close(a, ref, tol):
+    a = a.detach().double().cpu().numpy()
+    return np.abs(a - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+def _rel(a, ref):
+    a = a.detach().double().cpu().numpy()
+    return float(np.abs(a - ref).max() / max(1e-30, np.abs(ref).max()))
+
+
+def test_loaded_native_library():
+    import hint_b200
+    assert "sm_100a" in hint_b200.__version__
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_golden_forward_inverse(golden):
+    dev = torch.device("cuda:0")
+    meta = golden["meta"]
+    blk = _blk(meta).to(dev)
+    with torch.no_grad():
+        blk.flat.copy_(torch.from_numpy(golden["params"]))
+    x = torch.from_numpy(golden["x"]).to(dev)
+    cs = _split_c(golden.get("c"), meta["dims_c"], dev)
+    with torch.no_grad():
+        z = blk([x], c=cs)[0]
+        J = blk.jacobian([x], c=cs)
+        assert _close(z, golden["z64"], TOL) and _close(J, golden["J64"], TOL)
+        xi = blk([x], c=cs, rev=True)[0]
+        Ji = blk.jacobian(None)
+        assert _close(xi, golden["xinv64"], TOL) and _close(Ji, golden["Jinv64"], TOL)
+        xr = blk([z], c=cs, rev=True)[0]
+        assert _close(xr, golden["x"].astype(np.float64), 2e-5 * max(1.0, float(np.abs(golden["z64"]).max())))
+        assert _close(blk.jacobian(None) + J, np.zeros_like(golden["J64"]), 1e-4)
+
+
+def test_golden_training_gradients(golden):
+    """loss = 0.5*sum(z^2,1).mean() - J.mean() (train_unconditional.py:128-132) through autograd + the fused backward."""
+    dev = torch.device("cuda:0")
+    meta = golden["meta"]
+    blk = _blk(meta).to(dev)
+    with torch.no_grad():
+        blk.flat.copy_(torch.from_numpy(golden["params"]))
+    x = torch.from_numpy(golden["x"]).to(dev).requires_grad_(True)
+    cs = [c.requires_grad_(True) for c in _split_c(golden.get("c"), meta["dims_c"], dev)]
+    z = blk([x], c=cs)[0]
+    J = blk.jacobian([x], c=cs)
+    loss = 0.5 * torch.sum(z ** 2, dim=1).mean() - J.mean()
+    loss.backward()
+    assert abs(loss.item() - float(golden["loss64"])) <= 1e-5 * max(1.0, abs(float(golden["loss64"])))
+    assert _rel(x.grad, golden["dx64"]) < GTOL
+    assert _rel(blk.flat.grad, golden["dparams64"]) < GTOL
+    if cs:
+        assert _rel(torch.cat([c.grad for c in cs], dim=1), golden["dc64"]) < GTOL
+
+
+CONFIGS = [
+    # name, d, dc, c_internal, max_splits, B, weight scale
+    ("d43_hint_8", 43, 0, [67, 33, 16, 8], -1, 3000, 1.0),
+    ("miniboone_hint_4", 42, 0, [102, 51, 25, 12], -1, 1500, 1.0),
+    ("power_hint_8", 6, 0, [140, 70, 35, 17], -1, 4097, 1.0),
+    ("gas_hint_4", 8, 0, [184, 92, 46, 23], -1, 2000, 1.0),
+    ("lens_hint_8_full", 20, 0, [68, 34, 17, 17], -1, 2500, 1.0),
+    ("lens_concat_cond", 20, 2, [68, 34, 17, 17], -1, 1000, 1.0),
+    ("plus_hint_4_3", 100, 0, [314, 157, 78, 39], 3, 700, 1.0),
+    ("plus_hint_4_full", 100, 0, [263, 131, 65, 32, 32], -1, 500, 1.0),
+    ("plus_cond_recursive_4", 100, 4, [267, 133, 66], -1, 300, 0.5),
+    ("plus_hint_4_1", 100, 0, [358, 179], 1, 300, 1.0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c[0])
+def test_reference_configs_against_oracle(cfg):
+    """The block shapes of the reference configs at a batch the CPU oracle finishes in seconds."""
+    name, d, dc, ci, ms, B, wscale = cfg
+    dev = torch.device("cuda:0")
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    torch.manual_seed(1234)
+    blk = HierarchicalAffineCouplingBlock([(d,)], dims_c=[(dc,)] if dc else [], c_internal=list(ci), max_splits=ms)
+    with torch.no_grad():
+        blk.flat.mul_(wscale)
+    flat64 = blk.flat.detach().double().clone()
+    blk = blk.to(dev)
+    x = torch.randn(B, d)
+    c = torch.randn(B, dc) if dc else None
+    plan = O.build_plan(d, dc, ci, ms)
+    z_ref, J_ref = O.forward_fast(plan, flat64, x.double(), None if c is None else c.double())
+    xg = x.to(dev).requires_grad_(True)
+    cg = [c.to(dev).requires_grad_(True)] if dc else []
+    z = blk([xg], c=cg)[0]
+    J = blk.jacobian([xg], c=cg)
+    assert _close(z, z_ref.numpy(), TOL) and _close(J, J_ref.numpy(), TOL)
+    # gradients of the NLL loss vs the oracle's hand-written fp64 backward
+    loss = O.nll_loss(z, J)
+    loss.backward()
+    with torch.no_grad():
+        xr, dx, dcc, dflat = O.backward_from_output(plan, flat64, z_ref, None if c is None else c.double(), z_ref / B,
+                                                    torch.full((B,), -1.0 / B, dtype=torch.float64))
+    assert _rel(xg.grad, dx.numpy()) < GTOL
+    assert _rel(blk.flat.grad, dflat.numpy()) < GTOL
+    if dc:
+        assert _rel(cg[0].grad, dcc.numpy()) < GTOL
+    with torch.no_grad():
+        xi = blk([z.detach()], c=[t.detach() for t in cg], rev=True)[0]
+        assert _close(xi, x.double().numpy(), 5e-5 * max(1.0, float(z_ref.abs().max())))
+
+
+@pytest.mark.parametrize("B", [0, 1, 7, 127, 128, 129, 1000])
+def test_ragged_batches(B):
+    dev = torch.device("cuda:0")
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    torch.manual_seed(5)
+    blk = HierarchicalAffineCouplingBlock([(20,)], c_internal=[68, 34, 17, 17])
+    flat64 = blk.flat.detach().double().clone()
+    blk = blk.to(dev)
+    x = torch.randn(B, 20)
+    with torch.no_grad():
+        z = blk([x.to(dev)])[0]
+        J = blk.jacobian(None)
+    assert z.shape == (B, 20) and J.shape == (B,)
+    if B:
+        z_ref, J_ref = O.forward_fast(O.build_plan(20, 0, [68, 34, 17, 17]), flat64, x.double())
+        assert _close(z, z_ref.numpy(), TOL) and _close(J, J_ref.numpy(), TOL)
+
+
+def test_full_size_properties():
+    """BASELINE.json sizes (d=43, batch 256k): size-independent properties instead of the CPU oracle:
+    f^-1(f(x)) = x, J_rev(f(x)) = -J_fwd(x), determinism, and linearity of dparams in the upstream gradient."""
+    dev = torch.device("cuda:0")
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    torch.manual_seed(7)
+    B, d = 262144, 43
+    blk = HierarchicalAffineCouplingBlock([(d,)], c_internal=[67, 33, 16, 8]).to(dev)
+    x = torch.randn(B, d, device=dev)
+    with torch.no_grad():
+        z = blk([x])[0]
+        J = blk.jacobian(None)
+        z2 = blk([x])[0]
+        assert torch.equal(z, z2)
+        xr = blk([z], rev=True)[0]
+        Jr = blk.jacobian(None)
+    assert torch.isfinite(z).all()
+    assert (xr - x).abs().max().item() < 1e-4 * max(1.0, z.abs().max().item())
+    assert (J + Jr).abs().max().item() < 1e-4 * max(1.0, J.abs().max().item())
+    # backward: dparams is linear in (dz, dJ); the reconstructed input equals x
+    dz = torch.randn(B, d, device=dev) / B
+    dJ = torch.randn(B, device=dev) / B
+    dx1, _, g1, xrec = blk.plan.backward(z, None, blk.flat.detach(), dz, dJ, want_xrec=True)
+    dx2, _, g2, _ = blk.plan.backward(z, None, blk.flat.detach(), 2 * dz, 2 * dJ)
+    assert (xrec - x).abs().max().item() < 1e-4 * max(1.0, z.abs().max().item())
+    assert (g2 - 2 * g1).abs().max().item() <= 1e-5 * g1.abs().max().item() + 1e-7
+    assert (dx2 - 2 * dx1).abs().max().item() <= 1e-5 * dx1.abs().max().item() + 1e-9
+    dx3, _, g3, _ = blk.plan.backward(z, None, blk.flat.detach(), dz, dJ)
+    assert torch.equal(g1, g3) and torch.equal(dx1, dx3)   # deterministic reduction (no atomics)
