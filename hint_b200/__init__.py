@@ -5,9 +5,11 @@ Importing this package loads (building in-tree if needed) the sm_100a shared lib
 from . import _lib
 from .block import (HierarchicalAffineCouplingBlock, HierarchicalAffineCouplingTree, TreePlan,
                     linear_subnet_constructor, set_precision, get_precision)
+from .model import HintFlow, nll_loss
+from .parallel import BucketedGradAllReduce, broadcast_parameters, shard_rows
 
-_lib.load()
 __version__ = _lib.load().hint_version().decode()
 
 __all__ = ["HierarchicalAffineCouplingBlock", "HierarchicalAffineCouplingTree", "TreePlan",
-           "linear_subnet_constructor", "set_precision", "get_precision"]
+           "linear_subnet_constructor", "set_precision", "get_precision", "HintFlow", "nll_loss",
+           "BucketedGradAllReduce", "broadcast_parameters", "shard_rows"]

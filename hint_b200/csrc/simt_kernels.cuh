@@ -13,7 +13,12 @@ namespace hint {
 #if defined(__CUDA_ARCH__)
 #define HINT_PHASE(...) { const int tid = threadIdx.x; __VA_ARGS__; } __syncthreads();
 #else
-#define HINT_PHASE(...) for (int tid = 0; tid < kThreads; ++tid) { __VA_ARGS__; }
+// host emulation: visit the thread ids in a permuted order (stride coprime to 256) so an intra-phase dependency
+// between threads cannot hide behind sequential execution
+#ifndef HINT_EMUL_STRIDE
+#define HINT_EMUL_STRIDE 1
+#endif
+#define HINT_PHASE(...) for (int t_ = 0; t_ < kThreads; ++t_) { const int tid = (t_ * HINT_EMUL_STRIDE + 11) % kThreads; __VA_ARGS__; }
 #endif
 
 // One tile of TM samples through the whole tree: transport + log-det.

@@ -214,6 +214,63 @@ def forward_fast(plan: List[Node], flat: torch.Tensor, x: torch.Tensor, c: Optio
     return X, J
 
 
+def forward_blockwise(plan: List[Node], flat: torch.Tensor, x: torch.Tensor, c: Optional[torch.Tensor] = None,
+                      clamp: float = 4.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Forward direction with the reference's own op mix per node (views for the split, 6 addmm, one cat of
+    the node's columns - hint.py:68-90), autograd-friendly.  This is the CPU "port" that bench.py times as the
+    reference arm / cpu_baseline: same GEMM shapes, same elementwise passes and the same per-node concat copies."""
+    tab = _views(plan, flat)
+    alpha = clamp * SOFT_CLAMP_CONST
+    has_c = c is not None and c.shape[1] > 0
+    out = {}
+    Js = {}
+    for level in _levels(plan)[::-1]:
+        for n in level:
+            if n.leaf:
+                xu, xl = x[:, n.lo:n.lo + n.k], x[:, n.lo + n.k:n.hi]
+                Jc = None
+            else:
+                xu, xl = out.pop(n.upper), out.pop(n.lower)
+                Jc = Js.pop(n.upper) + Js.pop(n.lower)
+            a = torch.cat([xu, c], dim=1) if has_c else xu
+            s = _mlp(a, tab[n.idx], "s")
+            t = _mlp(a, tab[n.idx], "t")
+            xl = torch.exp(alpha * torch.atan(s)) * xl + t
+            Jn = torch.sum(alpha * torch.atan(s), dim=1)   # the reference evaluates atan twice (hint.py:57,60)
+            out[n.idx] = torch.cat([xu, xl], dim=1)
+            Js[n.idx] = Jn if Jc is None else Jc + Jn
+    return out[0], Js[0]
+
+
+def inverse_blockwise(plan: List[Node], flat: torch.Tensor, z: torch.Tensor, c: Optional[torch.Tensor] = None,
+                      clamp: float = 4.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rev=True direction with the reference's op mix (root coupling first, hint.py:79-94).  CPU timing port."""
+    tab = _views(plan, flat)
+    alpha = clamp * SOFT_CLAMP_CONST
+    has_c = c is not None and c.shape[1] > 0
+    inp = {0: z}
+    done = {}
+    J = torch.zeros(z.shape[0], dtype=z.dtype, device=z.device)
+    for level in _levels(plan):
+        for n in level:
+            xin = inp.pop(n.idx)
+            xu, xl = xin[:, :n.k], xin[:, n.k:]
+            a = torch.cat([xu, c], dim=1) if has_c else xu
+            s = _mlp(a, tab[n.idx], "s")
+            t = _mlp(a, tab[n.idx], "t")
+            xl = (xl - t) / torch.exp(alpha * torch.atan(s))
+            J = J - torch.sum(alpha * torch.atan(s), dim=1)
+            if n.leaf:
+                done[n.idx] = torch.cat([xu, xl], dim=1)
+            else:
+                inp[n.upper], inp[n.lower] = xu, xl
+    for level in _levels(plan)[::-1]:
+        for n in level:
+            if not n.leaf:
+                done[n.idx] = torch.cat([done.pop(n.upper), done.pop(n.lower)], dim=1)
+    return done[0], J
+
+
 def backward_from_output(plan: List[Node], flat: torch.Tensor, z: torch.Tensor, c: Optional[torch.Tensor],
                          dz: torch.Tensor, dJ: torch.Tensor, clamp: float = 4.0):
     """Memory-free backward of the *forward* direction, restated by hand (no autograd).

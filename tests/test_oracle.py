@@ -47,6 +47,20 @@ def test_forward_and_inverse_match_reference(golden):
             assert np.abs(Ji.detach().numpy() - golden["Jinv" + tag]).max() <= tol * max(1.0, float(np.abs(golden["Jinv" + tag]).max()))
 
 
+def test_blockwise_timing_ports_match_reference(golden):
+    plan, pk = _plan(golden["meta"])
+    dt = torch.float64
+    flat = torch.from_numpy(golden["params"]).to(dt)
+    x = torch.from_numpy(golden["x"]).to(dt)
+    c = torch.from_numpy(golden["c"]).to(dt) if "c" in golden else None
+    z, J = O.forward_blockwise(plan, flat, x, c, clamp=pk["clamp"])
+    assert np.abs(z.numpy() - golden["z64"]).max() <= 1e-12 * max(1.0, np.abs(golden["z64"]).max())
+    assert np.abs(J.numpy() - golden["J64"]).max() <= 1e-12 * max(1.0, np.abs(golden["J64"]).max())
+    xi, Ji = O.inverse_blockwise(plan, flat, x, c, clamp=pk["clamp"])
+    assert np.abs(xi.numpy() - golden["xinv64"]).max() <= 1e-12 * max(1.0, np.abs(golden["xinv64"]).max())
+    assert np.abs(Ji.numpy() - golden["Jinv64"]).max() <= 1e-12 * max(1.0, np.abs(golden["Jinv64"]).max())
+
+
 def _rel(a, b):
     return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
 
