@@ -2,6 +2,7 @@
 // plan's descriptor tables once per device, and launches the kernels on the caller's stream.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -9,7 +10,9 @@
 #include <string>
 
 #include "plan.h"
+#include "plan_tc.h"
 #include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
 
 using namespace hint;
 
@@ -37,8 +40,18 @@ struct DevSchedule {
     int max_ctas = 0;  // SMs x occupancy
 };
 
+struct DevTc {
+    TcStage* stages = nullptr;
+    TcOp* ops = nullptr;
+    TcChunk* chunks = nullptr;
+    TcFinal* fins = nullptr;
+    int* xlog = nullptr;
+    int* pack_src = nullptr;
+};
+
 struct DevPlan {
     DevSchedule fwd, bwd;
+    DevTc tc;
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
     int num_sms = 0;
@@ -48,6 +61,7 @@ struct DevPlan {
 
 struct hint_plan {
     Plan p;
+    TcSchedule tc;
     std::mutex mu;
     std::map<int, DevPlan> dev;  // per CUDA device ordinal
 };
@@ -66,7 +80,7 @@ cudaError_t upload(T** dst, const std::vector<T>& v) {
 template <int TM>
 cudaError_t setup_kernels(const Schedule& s, bool bwd, int num_sms, int* max_ctas) {
     const void* fn = bwd ? (const void*)hint_bwd_fp32_kernel<TM> : (const void*)hint_fwd_fp32_kernel<TM>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);  // per function, shared by all plans
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, s.smem_bytes);
@@ -110,6 +124,16 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     CUDA_TRY(setup_schedule(hp->p.bwd, true, d.num_sms, d.bwd));
     CUDA_TRY(upload(&d.pack_src, hp->p.pack_src));
     CUDA_TRY(upload(&d.unpack_src, hp->p.unpack_src));
+    if (hp->tc.ok) {
+        CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
+        CUDA_TRY(upload(&d.tc.ops, hp->tc.ops));
+        CUDA_TRY(upload(&d.tc.chunks, hp->tc.chunks));
+        CUDA_TRY(upload(&d.tc.fins, hp->tc.fins));
+        CUDA_TRY(upload(&d.tc.xlog, hp->tc.xlog));
+        CUDA_TRY(upload(&d.tc.pack_src, hp->tc.pack_src));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    }
     auto res = hp->dev.emplace(dev, d);
     *out = &res.first->second;
     return HINT_OK;
@@ -162,6 +186,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
         delete hp;
         return fail(code, err);
     }
+    build_tc_schedule(hp->p, hp->tc);
     *out = hp;
     return HINT_OK;
 }
@@ -177,6 +202,7 @@ void hint_plan_destroy(hint_plan_t* hp) {
             cudaFree(s->cgs); cudaFree(s->eps); cudaFree(s->dwjobs); cudaFree(s->stages);
         }
         cudaFree(d.pack_src); cudaFree(d.unpack_src);
+        cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
     delete hp;
@@ -209,8 +235,9 @@ int32_t hint_plan_tile_rows(const hint_plan_t* hp, int32_t which) {
 size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
     if (!hp || B < 0) { fail(HINT_ERR_INVALID, "bad plan or batch"); return 0; }
-    size_t bytes = align256((size_t)hp->p.n_packed * 4);
+    size_t bytes = align256((size_t)std::max<long long>(hp->p.n_packed, hp->tc.ok ? hp->tc.n_packed : 0) * 4);
     if (which == HINT_WS_BACKWARD) {
+        bytes = align256((size_t)hp->p.n_packed * 4);
         DevPlan* d = nullptr;
         if (get_dev(hp, &d) != HINT_OK) return 0;
         bytes += align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
@@ -221,8 +248,10 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
 static int check_common(const hint_plan* hp, const float* x, const float* c, const float* params, int64_t B, int32_t mode) {
     if (!hp) return fail(HINT_ERR_INVALID, "plan is NULL");
     if (B < 0) return fail(HINT_ERR_INVALID, "negative batch");
-    if (mode != HINT_MODE_FP32)
-        return fail(HINT_ERR_UNSUPPORTED, "only HINT_MODE_FP32 is built in this version (tcgen05 TF32 modes pending)");
+    if (mode == HINT_MODE_TF32X3) return fail(HINT_ERR_UNSUPPORTED, "HINT_MODE_TF32X3 is not built yet");
+    if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32) return fail(HINT_ERR_INVALID, "unknown mode");
+    if (mode == HINT_MODE_TF32 && !hp->tc.ok)
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the TF32 (tcgen05) kernel's envelope: " + hp->tc.why);
     if (B > 0 && (!x || !params)) return fail(HINT_ERR_INVALID, "NULL input pointer");
     if (B > 0 && hp->p.dc > 0 && !c) return fail(HINT_ERR_INVALID, "plan has a condition input but c is NULL");
     if (!aligned16(x) || !aligned16(c) || !aligned16(params)) return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
@@ -244,6 +273,30 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         return fail(HINT_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* packed = reinterpret_cast<float*>(workspace);
+    if (mode == HINT_MODE_TF32) {
+        const TcSchedule& t = hp->tc;
+        {
+            const int threads = 256;
+            const int blocks = (int)std::min<long long>((t.n_packed + threads - 1) / threads, 148 * 8);
+            hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats);
+            CUDA_TRY(cudaGetLastError());
+        }
+        TcDev T;
+        T.stages = d->tc.stages; T.ops = d->tc.ops; T.chunks = d->tc.chunks; T.fins = d->tc.fins; T.xlog = d->tc.xlog;
+        T.nstages = (int)t.stages.size(); T.nops = (int)t.ops.size(); T.nchunks = (int)t.chunks.size(); T.nfins = (int)t.fins.size();
+        T.d = t.d; T.dc = t.dc; T.xw = t.xw; T.xc = t.xc; T.xr = t.xr;
+        T.slot_bytes = t.slot_bytes; T.n_slots = t.n_slots;
+        T.smem_stage_in = t.smem_stage_in; T.smem_stage_bytes = t.smem_stage_bytes; T.smem_tables = t.smem_tables;
+        T.smem_bars = t.smem_bars; T.smem_ring = t.smem_ring;
+        T.alpha = hp->p.alpha;
+        T.round_acts = 1;
+        const long long ntiles = (B + 127) / 128;
+        const int grid = (int)std::min<long long>(ntiles, d->num_sms);
+        if (rev) hint_fwd_tf32_kernel<true><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
+        else hint_fwd_tf32_kernel<false><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
+        CUDA_TRY(cudaGetLastError());
+        return HINT_OK;
+    }
     if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
     const Schedule& s = hp->p.fwd;
     const DevTables T = make_tables(hp->p, s, d->fwd);
@@ -266,7 +319,9 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
                   const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
                   void* workspace, size_t workspace_bytes, void* stream) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
-    int rc = check_common(hp, z, c, params, B, mode);
+    // The backward sweep currently always runs the FP32 CUDA-core kernel (also in TF32 mode, where it
+    // differentiates the exact function at the TF32-computed output).
+    int rc = check_common(hp, z, c, params, B, mode == HINT_MODE_TF32 ? HINT_MODE_FP32 : mode);
     if (rc != HINT_OK) return rc;
     if (!dparams) return fail(HINT_ERR_INVALID, "dparams is NULL");
     cudaStream_t st = (cudaStream_t)stream;
