@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -290,11 +291,30 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         T.smem_bars = t.smem_bars; T.smem_ring = t.smem_ring;
         T.alpha = hp->p.alpha;
         T.round_acts = 1;
+        T.bias_base = (int)t.n_weight_floats;
+        T.n_bias = (int)(t.n_packed - t.n_weight_floats);
+        T.dbg = nullptr;
+        static long long* dbg_buf = nullptr;   // HINT_B200_TC_DEBUG=1: cycle breakdown of CTA 0, printed after a sync
+        const bool dbg = std::getenv("HINT_B200_TC_DEBUG") != nullptr;
+        if (dbg) {
+            if (!dbg_buf) CUDA_TRY(cudaMalloc((void**)&dbg_buf, 16 * sizeof(long long)));
+            CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st));
+            T.dbg = dbg_buf;
+        }
         const long long ntiles = (B + 127) / 128;
         const int grid = (int)std::min<long long>(ntiles, d->num_sms);
         if (rev) hint_fwd_tf32_kernel<true><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
         else hint_fwd_tf32_kernel<false><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
         CUDA_TRY(cudaGetLastError());
+        if (dbg) {
+            long long h[16];
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+            const double nt = (double)std::max<long long>(1, h[6]);
+            std::fprintf(stderr, "[hint_b200 tc dbg] tiles/CTA %lld | issuer0 cycles/tile: wait_tile %.0f wait_prev_final %.0f wait_epi %.0f wait_chunk %.0f issue %.0f walk %.0f"
+                         " | epilogue warp0 cycles/tile: load %.0f wait_mma %.0f hidden %.0f wait_fin %.0f final %.0f store %.0f\n",
+                         h[6], h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
+        }
         return HINT_OK;
     }
     if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;

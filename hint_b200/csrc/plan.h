@@ -12,7 +12,7 @@
 
 namespace hint {
 
-constexpr int kThreads = 256;          // threads per CTA of the SIMT kernels
+constexpr int kThreads = 512;          // threads per CTA of the SIMT kernels
 constexpr int kSmemMax = 227 * 1024;   // usable shared memory per CTA on sm_100
 
 // ---- device-visible POD descriptors -------------------------------------------------------------

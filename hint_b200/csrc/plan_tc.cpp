@@ -93,7 +93,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
 
     std::vector<int32_t> wsrc;   // weight images
     std::vector<int32_t> bsrc;   // biases (appended after the weights)
-    auto alloc_bias = [&](int n) { int o = (int)bsrc.size(); bsrc.resize(bsrc.size() + n, -1); return o; };
+    auto alloc_bias = [&](int n) { int o = (int)bsrc.size(); bsrc.resize(bsrc.size() + ((n + 3) & ~3), -1); return o; };
 
     for (const auto& g : groups) {
         TcStage st{};
@@ -129,6 +129,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
         int job_last_op[TC_NJOBS];
         for (int& v : job_last_op) v = -1;
         bool bad = false;
+        int issuer_load[TC_NJOBS][kTcIssuers] = {};
         // emit D[:, d_col .. d_col+n_rows) (+)= A[:, a_col .. a_col+8nk) * B^T with B(n,k) = params[fill(n,k)] (or 0)
         auto emit = [&](int job, int d_col, int a_col, int n_rows, int nk, bool accum, const std::function<long long(int, int)>& fill) {
             if (nk == 0) return;
@@ -155,6 +156,15 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
                 if (accum) op.flags |= TC_ACCUM;
                 op.wait_epi = -1;
                 op.commit_job = -1;
+                if (accum && !t.ops.empty()) {
+                    op.issuer = t.ops.back().issuer;       // accumulates onto the previous op's D: same thread, program order
+                } else {
+                    int best = 0;
+                    for (int q = 1; q < kTcIssuers; ++q)
+                        if (issuer_load[job][q] < issuer_load[job][best]) best = q;
+                    op.issuer = (unsigned char)best;
+                }
+                issuer_load[job][op.issuer] += nk + 2;
                 const size_t base = wsrc.size();
                 wsrc.resize(base + (size_t)rows * kpad, -1);
                 for (int r = 0; r < rows; ++r)
@@ -263,7 +273,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
             st.has_job[j] = job_first_op[j] >= 0;
             if (!st.has_job[j]) continue;
             t.ops[job_first_op[j]].wait_epi = (short)dep[j];
-            t.ops[job_last_op[j]].commit_job = (short)j;
+            t.ops[job_last_op[j]].commit_job = (signed char)j;
         }
         if (!st.has_job[TC_J2T]) st.hid[2].ncols = 0;
         st.op_end = (int)t.ops.size();
@@ -277,6 +287,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
     t.pack_src = wsrc;
     t.pack_src.insert(t.pack_src.end(), bsrc.begin(), bsrc.end());
     while (t.pack_src.size() % 4) t.pack_src.push_back(-1);
+    if (t.n_weight_floats % 4) return fail("internal: weight images must be 16-byte multiples");
     t.n_packed = (long long)t.pack_src.size();
     const int boff = (int)t.n_weight_floats;
     for (auto& st : t.stages)
@@ -288,7 +299,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
     t.smem_stage_in = off; t.smem_stage_bytes = stage_bytes; off += 2 * stage_bytes;
     t.smem_tables = off;
     t.smem_tables_bytes = (int)(t.stages.size() * sizeof(TcStage) + t.ops.size() * sizeof(TcOp) + t.chunks.size() * sizeof(TcChunk) +
-                                t.fins.size() * sizeof(TcFinal) + t.xw * 4 + 64);
+                                t.fins.size() * sizeof(TcFinal) + t.xw * 4 + 64 + (t.n_packed - t.n_weight_floats) * 4);
     t.smem_tables_bytes = (t.smem_tables_bytes + 127) & ~127;
     off += t.smem_tables_bytes;
     t.smem_bars = off;

@@ -20,6 +20,7 @@
 namespace hint {
 
 enum { TC_ACCUM = 1, TC_FIRST_IN_CHUNK = 2, TC_LAST_IN_CHUNK = 4 };
+constexpr int kTcIssuers = 4;
 enum { TC_J1 = 0, TC_J2S = 1, TC_J2T = 2, TC_J3S = 3, TC_J3T = 4, TC_NJOBS = 5 };
 
 struct TcOp {                 // D[128 x N] (+)= A[128 x 8*nk] * B[N x 8*nk]^T
@@ -30,7 +31,8 @@ struct TcOp {                 // D[128 x N] (+)= A[128 x 8*nk] * B[N x 8*nk]^T
     int n_rows;               // N (for the emulator)
     int flags;                // TC_*
     short wait_epi;           // job of THIS stage whose epilogue must be complete before issue, or -1
-    short commit_job;         // job completed by this op (tcgen05.commit -> mma_done[job]), or -1
+    signed char commit_job;   // job completed by this op (every issuer commits -> mma_done[job]), or -1
+    unsigned char issuer;     // which of the kTcIssuers MMA warps issues this op (issue cost ~80 cycles/MMA per thread)
 };
 
 struct TcChunk {              // contiguous piece of the packed weight image, copied into one ring slot

@@ -4,8 +4,10 @@
 //   warps 0-7  epilogue: TMEM -> registers -> TMEM (bias + ReLU in place), the coupling epilogue
 //              (atan soft clamp, exp, affine, log-det) and the tile load / store.  Warp w owns TMEM
 //              lanes 32*(w%4)..+31; warps 0-3 and 4-7 split the columns of every job.
-//   warp 8     MMA issuer: one elected thread issues every tcgen05.mma (A from TMEM, B from the ring).
-//   warp 9     weight producer: one elected thread streams the packed weight images from L2 into a
+//   warps 8-11 MMA issuers: one elected thread each; the ops of every job are split between them because a
+//              single thread sustains only ~1 tcgen05.mma per 80 cycles (measured: tests/cuda/umma_bench2.cu),
+//              4 warps ~1 per 27 cycles.  A from TMEM, B from the ring.
+//   warp 12    weight producer: one elected thread streams the packed weight images from L2 into a
 //              shared-memory ring with 1-D bulk copies (mbarrier complete_tx).
 // All hand-offs are mbarriers: ring full/empty, mma_done[stage][job] (tcgen05.commit), epi_done[stage][job].
 #pragma once
@@ -14,7 +16,7 @@
 
 namespace hint {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 256 + 32 * kTcIssuers + 32;   // 8 epilogue warps, kTcIssuers MMA warps, 1 producer warp
 constexpr int kTcEpiThreads = 256;
 
 struct TcDev {
@@ -29,7 +31,12 @@ struct TcDev {
     int smem_stage_in, smem_stage_bytes, smem_tables, smem_bars, smem_ring;
     float alpha;
     int round_acts;   // round activations to tf32 (rna) in the epilogue instead of letting the MMA truncate
+    int bias_base;    // first bias float in the packed buffer (== number of weight floats)
+    int n_bias;
+    long long* dbg;   // optional cycle breakdown of CTA 0 (nullptr in production)
 };
+
+#define HINT_TC_T(var) do { if (T.dbg) { long long now_ = clock64(); (var) += now_ - tmark; tmark = now_; } } while (0)
 
 template <bool kRev>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -47,6 +54,7 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
     TcChunk* s_chunks = reinterpret_cast<TcChunk*>(s_ops + T.nops);
     TcFinal* s_fins = reinterpret_cast<TcFinal*>(s_chunks + T.nchunks);
     int* s_xlog = reinterpret_cast<int*>(s_fins + T.nfins);
+    float* s_bias = reinterpret_cast<float*>(s_xlog + ((T.xw + 3) & ~3));   // all biases of the block (16-byte aligned)
     {
         const int n1 = T.nstages * (int)(sizeof(TcStage) / 4), n2 = T.nops * (int)(sizeof(TcOp) / 4),
                   n3 = T.nchunks * (int)(sizeof(TcChunk) / 4), n4 = T.nfins * (int)(sizeof(TcFinal) / 4);
@@ -55,6 +63,7 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
         for (int i = tid; i < n3; i += kTcThreads) reinterpret_cast<int*>(s_chunks)[i] = reinterpret_cast<const int*>(T.chunks)[i];
         for (int i = tid; i < n4; i += kTcThreads) reinterpret_cast<int*>(s_fins)[i] = reinterpret_cast<const int*>(T.fins)[i];
         for (int i = tid; i < T.xw; i += kTcThreads) s_xlog[i] = T.xlog[i];
+        for (int i = tid; i < T.n_bias; i += kTcThreads) s_bias[i] = W[T.bias_base + i];
     }
     // ---- barriers ----
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.smem_bars);
@@ -64,9 +73,9 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
     uint64_t* bar_mma = bar_tile + 1;                     // [stage][5]
     uint64_t* bar_epi = bar_mma + T.nstages * TC_NJOBS;   // [stage][4]  (0..2 hidden, 3 final)
     if (tid == 0) {
-        for (int i = 0; i < T.n_slots; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, 1); }
+        for (int i = 0; i < T.n_slots; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, kTcIssuers); }
         mbar_init(bar_tile, 8);
-        for (int i = 0; i < T.nstages * TC_NJOBS; ++i) mbar_init(bar_mma + i, 1);
+        for (int i = 0; i < T.nstages * TC_NJOBS; ++i) mbar_init(bar_mma + i, kTcIssuers);
         for (int i = 0; i < T.nstages * 4; ++i) mbar_init(bar_epi + i, 8);
         fence_mbar_init();
     }
@@ -77,8 +86,9 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
     const uint32_t tbase = tmem_slot;
     const long long ntiles = (B + 127) / 128;
     unsigned char* ring = smem + T.smem_ring;
+    const uint32_t ring_u32 = smem_u32(ring);
 
-    if (warp == 9) {
+    if (warp == 8 + kTcIssuers) {
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t cnt = 0;
@@ -96,14 +106,17 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
                 }
             }
         }
-    } else if (warp == 8) {
-        // ================= MMA issuer =================
+    } else if (warp >= 8) {
+        // ================= MMA issuers =================
         if (lane == 0) {
+            const int me = warp - 8;
             uint32_t cnt = 0, it = 0;
+            long long t_tile = 0, t_prev = 0, t_epi = 0, t_chunk = 0, t_issue = 0, t_walk = 0, tmark = clock64();
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const uint32_t tp = it & 1;
                 mbar_wait(bar_tile, tp);
                 fence_after_sync();
+                HINT_TC_T(t_tile);
                 int prev = -1;
                 for (int si = 0; si < T.nstages; ++si) {
                     const int s = kRev ? si : T.nstages - 1 - si;
@@ -111,29 +124,43 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
                     if (prev >= 0) {  // x columns written by the previous stage's coupling epilogue
                         mbar_wait(bar_epi + prev * 4 + 3, tp);
                         fence_after_sync();
+                        HINT_TC_T(t_prev);
                     }
                     uint32_t slot = 0;
+                    bool chunk_ready = false;
                     for (int oi = st.op_begin; oi < st.op_end; ++oi) {
                         const TcOp op = s_ops[oi];
-                        if (op.flags & TC_FIRST_IN_CHUNK) {
-                            slot = cnt % T.n_slots;
-                            mbar_wait(bar_full + slot, (cnt / T.n_slots) & 1);
-                        }
+                        if (op.flags & TC_FIRST_IN_CHUNK) { slot = cnt % T.n_slots; chunk_ready = false; }
+                        HINT_TC_T(t_walk);
                         if (op.wait_epi >= 0) {
                             mbar_wait(bar_epi + s * 4 + op.wait_epi, tp);
                             fence_after_sync();
+                            HINT_TC_T(t_epi);
                         }
-                        const uint32_t b_addr = smem_u32(ring + (size_t)slot * T.slot_bytes) + (uint32_t)op.b_off * 4;
-                        const uint32_t sbo = (uint32_t)op.nk * 256;
+                        if (op.issuer == me) {
+                        if (!chunk_ready) { mbar_wait(bar_full + slot, (cnt / T.n_slots) & 1); chunk_ready = true; HINT_TC_T(t_chunk); }
+                        // B descriptor: lo = (addr >> 4) | (LBO=128 >> 4) << 16 ; hi = (SBO = nk*256 >> 4) | version 1 (bit 46)
+                        uint32_t b_lo = ((ring_u32 + slot * (uint32_t)T.slot_bytes + (uint32_t)op.b_off * 4) >> 4) | (8u << 16);
+                        const uint32_t b_hi = ((uint32_t)op.nk * 16) | (1u << 14);
+                        uint32_t a_t = tbase + op.a_col;
+                        const uint32_t d_t = tbase + op.d_col;
+                        uint32_t acc = (op.flags & TC_ACCUM) ? 1u : 0u;
                         for (int ks = 0; ks < op.nk; ++ks) {
-                            const uint64_t bd = smem_desc(b_addr + ks * 256, 128, sbo);
-                            mma_ts(tbase + op.d_col, tbase + op.a_col + ks * 8, bd, op.idesc, (ks > 0) || (op.flags & TC_ACCUM));
+                            mma_ts(d_t, a_t, ((uint64_t)b_hi << 32) | b_lo, op.idesc, acc);
+                            b_lo += 16;   // two core matrices (256 B) along K
+                            a_t += 8;
+                            acc = 1u;
+                        }
+                        HINT_TC_T(t_issue);
                         }
                         if (op.commit_job >= 0) commit(bar_mma + s * TC_NJOBS + op.commit_job);
                         if (op.flags & TC_LAST_IN_CHUNK) { commit(bar_empty + slot); ++cnt; }
                     }
                     prev = s;
                 }
+            }
+            if (T.dbg && blockIdx.x == 0 && me == 0) {
+                T.dbg[0] = t_tile; T.dbg[1] = t_prev; T.dbg[2] = t_epi; T.dbg[3] = t_chunk; T.dbg[4] = t_issue; T.dbg[5] = t_walk; T.dbg[6] = it;
             }
         }
     } else {
@@ -145,6 +172,7 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
         float* stg_c = stg + 128 * T.d;
         float* jx = reinterpret_cast<float*>(smem + T.smem_stage_in + T.smem_stage_bytes);  // 128 floats of scratch
         uint32_t it = 0;
+        long long e_load = 0, e_waitmma = 0, e_hid = 0, e_waitfin = 0, e_fin = 0, e_store = 0, tmark = clock64();
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t tp = it & 1;
             const long long row0 = tile * 128;
@@ -181,6 +209,7 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tile);
+            HINT_TC_T(e_load);
             float jacc = 0.f;
             for (int si = 0; si < T.nstages; ++si) {
                 const int s = kRev ? si : T.nstages - 1 - si;
@@ -191,39 +220,47 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
                     if (h.ncols == 0) continue;
                     mbar_wait(bar_mma + s * TC_NJOBS + j, tp);
                     fence_after_sync();
-                    const float* bias = W + h.bias_off;
-                    for (int q = 8 * wg; q < h.ncols; q += 16) {
-                        float v[8];
+                    HINT_TC_T(e_waitmma);
+                    const float* bias = s_bias + (h.bias_off - T.bias_base);
+                    for (int q = 16 * wg; q < h.ncols; q += 32) {
+                        float v[16];
                         const uint32_t a = tbase + lane_base + h.col0 + q;
-                        ld8(a, v);
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + q));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + q + 4));
-                        wait_ld();
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        ld16(a, v);
+                        float bb[16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float r = fmaxf(v[e] + bb[e], 0.f);
-                            v[e] = T.round_acts ? to_tf32(r) : r;
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + q + e);
+                            bb[e] = b.x; bb[e + 1] = b.y; bb[e + 2] = b.z; bb[e + 3] = b.w;
                         }
-                        st8(a, v);
+                        wait_ld();
+                        if (T.round_acts) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) v[e] = to_tf32(fmaxf(v[e] + bb[e], 0.f));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e] + bb[e], 0.f);
+                        }
+                        st16(a, v);
                     }
                     wait_st();
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_epi + s * 4 + j);
+                    HINT_TC_T(e_hid);
                 }
                 // coupling epilogue (hint.py:79-84) on the lower-half x columns
                 if (st.has_job[TC_J3S]) mbar_wait(bar_mma + s * TC_NJOBS + TC_J3S, tp);
                 if (st.has_job[TC_J3T]) mbar_wait(bar_mma + s * TC_NJOBS + TC_J3T, tp);
                 fence_after_sync();
+                HINT_TC_T(e_waitfin);
                 for (int fi = st.fin_begin + wg; fi < st.fin_end; fi += 2) {
                     const TcFinal f = s_fins[fi];
                     float sv[4], tv[4], xv[4];
                     ld4(tbase + lane_base + f.s_col, sv);
                     ld4(tbase + lane_base + f.t_col, tv);
                     ld4(tbase + lane_base + f.x_col, xv);
-                    const float4 bs = __ldg(reinterpret_cast<const float4*>(W + f.bs_off));
-                    const float4 bt = __ldg(reinterpret_cast<const float4*>(W + f.bt_off));
+                    const float4 bs = *reinterpret_cast<const float4*>(s_bias + (f.bs_off - T.bias_base));
+                    const float4 bt = *reinterpret_cast<const float4*>(s_bias + (f.bt_off - T.bias_base));
                     wait_ld();
                     const float bsv[4] = {bs.x, bs.y, bs.z, bs.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
 #pragma unroll
@@ -239,6 +276,7 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_epi + s * 4 + 3);
+                HINT_TC_T(e_fin);
             }
             // ---- TMEM x columns -> staging rows -> global (coalesced) ----
             named_bar_sync(1, kTcEpiThreads);   // the other half's coupling writes to this row's columns
@@ -266,6 +304,10 @@ hint_fwd_tf32_kernel(TcDev T, const float* __restrict__ x, const float* __restri
                 if (wg == 0 && row < rows) logdet[row0 + row] = jacc + jx[row];
             }
             named_bar_sync(1, kTcEpiThreads);
+            HINT_TC_T(e_store);
+        }
+        if (T.dbg && blockIdx.x == 0 && tid == 0) {
+            T.dbg[8] = e_load; T.dbg[9] = e_waitmma; T.dbg[10] = e_hid; T.dbg[11] = e_waitfin; T.dbg[12] = e_fin; T.dbg[13] = e_store; T.dbg[14] = it;
         }
     }
     fence_before_sync();
