@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhint_b200.so")
 SOURCES = ["plan.cpp", "plan_tc.cpp", "capi.cu"]
-HEADERS = ["plan.h", "plan_tc.h", "tcgen05.cuh", "tc_kernels.cuh", "simt_phases.cuh", "simt_kernels.cuh", os.path.join("..", "..", "include", "hint_b200.h")]
+HEADERS = ["plan.h", "plan_tc.h", "tcgen05.cuh", "tc_kernels.cuh", "tc2_kernels.cuh", "simt_phases.cuh", "simt_kernels.cuh", os.path.join("..", "..", "include", "hint_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -14,6 +14,7 @@
 #include "plan_tc.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc2_kernels.cuh"
 
 using namespace hint;
 
@@ -63,6 +64,7 @@ struct DevPlan {
 struct hint_plan {
     Plan p;
     TcSchedule tc;
+    T2Host tc2;
     std::mutex mu;
     std::map<int, DevPlan> dev;  // per CUDA device ordinal
 };
@@ -134,6 +136,8 @@ int get_dev(hint_plan* hp, DevPlan** out) {
         CUDA_TRY(upload(&d.tc.pack_src, hp->tc.pack_src));
         CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     }
     auto res = hp->dev.emplace(dev, d);
     *out = &res.first->second;
@@ -188,6 +192,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
         return fail(code, err);
     }
     build_tc_schedule(hp->p, hp->tc);
+    build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
     return HINT_OK;
 }
@@ -281,6 +286,31 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
             const int blocks = (int)std::min<long long>((t.n_packed + threads - 1) / threads, 148 * 8);
             hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats);
             CUDA_TRY(cudaGetLastError());
+        }
+        static const bool force_v1 = std::getenv("HINT_B200_TC_V1") != nullptr;
+        if (hp->tc2.ok && !force_v1) {
+            const long long ntiles = (B + 127) / 128;
+            const int grid = (int)std::min<long long>(ntiles, d->num_sms);
+            static long long* dbg2 = nullptr;   // HINT_B200_TC_DEBUG=1: cycle breakdown of CTA 0, printed after a sync
+            static const bool dbg_on = std::getenv("HINT_B200_TC_DEBUG") != nullptr;
+            if (dbg_on) {
+                if (!dbg2) CUDA_TRY(cudaMalloc((void**)&dbg2, 16 * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(dbg2, 0, 16 * sizeof(long long), st));
+            }
+            long long* dp = dbg_on ? dbg2 : nullptr;
+            if (rev) hint_tc2_kernel<true><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp);
+            else hint_tc2_kernel<false><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp);
+            CUDA_TRY(cudaGetLastError());
+            if (dbg_on) {
+                long long h[16];
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaMemcpy(h, dbg2, sizeof(h), cudaMemcpyDeviceToHost));
+                const double nt = (double)std::max<long long>(1, h[6]);
+                std::fprintf(stderr, "[hint_b200 tc2 dbg] tiles/CTA %lld | issuer0 cyc/tile: wait_tile %.0f wait_prev_final %.0f wait_epi %.0f wait_chunk %.0f issue %.0f"
+                             " | epi warp0 cyc/tile: wait_x %.0f load %.0f wait_mma %.0f hidden %.0f wait_fin %.0f final %.0f store %.0f\n",
+                             h[6], h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt, h[14] / nt);
+            }
+            return HINT_OK;
         }
         TcDev T;
         T.stages = d->tc.stages; T.ops = d->tc.ops; T.chunks = d->tc.chunks; T.fins = d->tc.fins; T.xlog = d->tc.xlog;

@@ -2,6 +2,7 @@
 #include "plan_tc.h"
 
 #include <algorithm>
+#include <cstring>
 #include <functional>
 
 namespace hint {
@@ -155,6 +156,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
                 op.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(rows >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
                 if (accum) op.flags |= TC_ACCUM;
                 op.wait_epi = -1;
+                op.job = (signed char)job;
                 op.commit_job = -1;
                 if (accum && !t.ops.empty()) {
                     op.issuer = t.ops.back().issuer;       // accumulates onto the previous op's D: same thread, program order
@@ -272,7 +274,7 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
         for (int j = 0; j < TC_NJOBS; ++j) {
             st.has_job[j] = job_first_op[j] >= 0;
             if (!st.has_job[j]) continue;
-            t.ops[job_first_op[j]].wait_epi = (short)dep[j];
+            t.ops[job_first_op[j]].wait_epi = (signed char)dep[j];
             t.ops[job_last_op[j]].commit_job = (signed char)j;
         }
         if (!st.has_job[TC_J2T]) st.hid[2].ncols = 0;
@@ -312,6 +314,105 @@ void build_tc_schedule(const Plan& p, TcSchedule& t) {
     t.smem_bytes = (size_t)off;
     if (t.stages.size() * 9 + 2 * 4 + 1 > 250) return fail("too many stages for the barrier table");
     t.ok = true;
+}
+
+// ---- v2 encoding -----------------------------------------------------------------------------------------------
+void build_tc2_program(const Plan& p, const TcSchedule& t, T2Host& out) {
+    out.ok = false;
+    out.why.clear();
+    out.smem_bytes = 0;
+    if (!t.ok) { out.why = t.why; return; }
+    T2Prog& P = out.prog;
+    std::memset(&P, 0, sizeof(P));
+    auto fail = [&](const std::string& why) { out.ok = false; out.why = why; };
+    if ((int)t.stages.size() > kT2MaxStages || (int)t.ops.size() > kT2MaxOps || (int)t.fins.size() > kT2MaxFins ||
+        (int)t.chunks.size() > kT2MaxChunks || t.xw > kT2MaxXw)
+        return fail("program too large for the kernel-parameter space of the TF32 kernel");
+    P.nstages = (int)t.stages.size();
+    P.nfins = (int)t.fins.size();
+    P.d = t.d; P.dc = t.dc; P.xw = t.xw; P.xc = t.xc; P.xr = t.xr;
+    P.slot_bytes = t.slot_bytes;
+    P.bias_base = (int)t.n_weight_floats;
+    P.n_bias = (int)(t.n_packed - t.n_weight_floats);
+    P.alpha = p.alpha;
+    P.round_acts = 1;
+    for (int i = 0; i < t.xw; ++i) P.xlog[i] = (int16_t)t.xlog[i];
+    for (size_t i = 0; i < t.chunks.size(); ++i) {
+        if (t.chunks[i].g_off % 4 || t.chunks[i].bytes % 16) return fail("internal: unaligned weight chunk");
+        P.chunks[i] = T2Chunk{(uint32_t)(t.chunks[i].g_off / 4), (uint32_t)t.chunks[i].bytes};
+    }
+    for (size_t i = 0; i < t.fins.size(); ++i) {
+        const TcFinal& f = t.fins[i];
+        P.fins[i] = T2Fin{(uint16_t)f.s_col, (uint16_t)f.t_col, (uint16_t)f.x_col, (uint16_t)(f.bs_off - P.bias_base), (uint16_t)(f.bt_off - P.bias_base)};
+    }
+    if (P.n_bias > 65535) return fail("too many biases for the 16-bit offsets of the TF32 program");
+    int nseg = 0, nop = 0;
+    for (int s = 0; s < P.nstages; ++s) {
+        const TcStage& st = t.stages[s];
+        T2Stage& S = P.stages[s];
+        S.seg_begin = (uint16_t)nseg;
+        S.fin_begin = (uint16_t)st.fin_begin; S.fin_end = (uint16_t)st.fin_end;
+        S.chunk_begin = (uint16_t)st.chunk_begin; S.chunk_end = (uint16_t)st.chunk_end;
+        for (int j = 0; j < 3; ++j)
+            S.hid[j] = T2Hidden{(uint16_t)st.hid[j].col0, (uint16_t)st.hid[j].ncols, (uint16_t)(st.hid[j].ncols ? st.hid[j].bias_off - P.bias_base : 0), 0};
+        // runs of ops with the same (job, chunk); every job gets at least one (possibly empty) segment so that every
+        // barrier of the kernel completes exactly once per stage
+        int oi = st.op_begin;
+        for (int job = 0; job < TC_NJOBS; ++job) {
+            bool first = true;
+            int last_seg = -1;
+            while (oi < st.op_end && t.ops[oi].job == job) {
+                int oe = oi + 1;
+                while (oe < st.op_end && t.ops[oe].job == job && !(t.ops[oe].flags & TC_FIRST_IN_CHUNK)) ++oe;
+                if (nseg >= kT2MaxSegs) return fail("program too large for the kernel-parameter space of the TF32 kernel");
+                T2Seg& G = P.segs[nseg];
+                G.job = (uint8_t)job;
+                G.flags = (uint8_t)((first ? T2_FIRST_IN_JOB : 0) | ((t.ops[oi].flags & TC_FIRST_IN_CHUNK) ? T2_FIRST_IN_CHUNK : 0) |
+                                    ((t.ops[oe - 1].flags & TC_LAST_IN_CHUNK) ? T2_LAST_IN_CHUNK : 0));
+                for (int q = 0; q < kTcIssuers; ++q) {
+                    G.op_ofs[q] = (uint16_t)nop;
+                    for (int o = oi; o < oe; ++o) {
+                        const TcOp& op = t.ops[o];
+                        if (op.issuer != q) continue;
+                        if ((op.b_off * 4) % 16) return fail("internal: unaligned weight image");
+                        const uint32_t sbo = (uint32_t)op.nk * 256;   // 8 rows x (8*nk) floats
+                        P.ops[nop++] = T2Op{(uint32_t)op.d_col | ((uint32_t)op.a_col << 16), (uint32_t)(op.b_off * 4) >> 4,
+                                            (sbo >> 4) | ((uint32_t)op.nk << 16), op.idesc | ((op.flags & TC_ACCUM) ? 1u : 0u)};
+                    }
+                }
+                G.op_ofs[kTcIssuers] = (uint16_t)nop;
+                first = false;
+                last_seg = nseg++;
+                oi = oe;
+            }
+            if (last_seg < 0) {
+                if (nseg >= kT2MaxSegs) return fail("program too large for the kernel-parameter space of the TF32 kernel");
+                T2Seg& G = P.segs[nseg];
+                for (int q = 0; q <= kTcIssuers; ++q) G.op_ofs[q] = (uint16_t)nop;
+                G.job = (uint8_t)job;
+                G.flags = T2_FIRST_IN_JOB;
+                last_seg = nseg++;
+            }
+            P.segs[last_seg].flags |= T2_LAST_IN_JOB;
+        }
+        if (oi != st.op_end) return fail("internal: ops of a stage are not ordered by job");
+        S.seg_end = (uint16_t)nseg;
+    }
+    // ---- shared memory: [barriers 1 KB][epilogue tables][biases][x/c staging in x2][z staging + log-det scratch][ring] ----
+    int off = 1024;
+    P.smem_tab = off;   // copies of the epilogue tables: stages | fins | xlog
+    off += (int)((P.nstages * sizeof(T2Stage) + P.nfins * sizeof(T2Fin) + t.xw * sizeof(int16_t) + 127) & ~size_t(127)) + 128;
+    P.smem_bias = off; off += ((P.n_bias * 4) + 127) & ~127;
+    P.smem_in_bytes = ((128 * (t.d + t.dc) * 4) + 127) & ~127;
+    P.smem_in = off; off += 2 * P.smem_in_bytes;
+    P.smem_out = off; off += ((128 * t.d * 4 + 512) + 127) & ~127;
+    off = (off + 1023) & ~1023;
+    P.smem_ring = off;
+    P.n_slots = std::min(6, (kSmemMax - off) / t.slot_bytes);
+    if (P.n_slots < 2) return fail("not enough shared memory for a double-buffered weight ring");
+    off += P.n_slots * t.slot_bytes;
+    out.smem_bytes = (size_t)off;
+    out.ok = true;
 }
 
 }  // namespace hint

@@ -30,7 +30,8 @@ struct TcOp {                 // D[128 x N] (+)= A[128 x 8*nk] * B[N x 8*nk]^T
     unsigned idesc;           // tcgen05 instruction descriptor (tf32, M=128, N)
     int n_rows;               // N (for the emulator)
     int flags;                // TC_*
-    short wait_epi;           // job of THIS stage whose epilogue must be complete before issue, or -1
+    signed char wait_epi;     // job of THIS stage whose epilogue must be complete before issue, or -1
+    signed char job;          // TC_J* this op belongs to
     signed char commit_job;   // job completed by this op (every issuer commits -> mma_done[job]), or -1
     unsigned char issuer;     // which of the kTcIssuers MMA warps issues this op (issue cost ~80 cycles/MMA per thread)
 };
@@ -91,6 +92,56 @@ struct TcSchedule {
 
 // Builds the TF32 program for a plan (after build_plan).  Never fails hard: !ok + why when outside the envelope.
 void build_tc_schedule(const Plan& p, TcSchedule& t);
+
+// ---- v2 program: the same schedule, re-encoded for the kernel of tc2_kernels.cuh ---------------------------------
+// The whole program is passed BY VALUE as a __grid_constant__ kernel parameter, so the MMA-issuing threads fetch
+// their operands with uniform constant-bank loads (measured: 38 cycles per tcgen05.mma with warp-uniform
+// operands against 77 when the compiler has to wrap the instruction in a divergence "waterfall" loop;
+// profiles/ubench3_r01_mma_issue_tmem.txt).  Ops are pre-partitioned per issuing warp, so nobody walks ops it
+// does not own.
+constexpr int kT2MaxOps = 1000, kT2MaxSegs = 288, kT2MaxStages = 48, kT2MaxFins = 400, kT2MaxChunks = 96, kT2MaxXw = 192;
+enum { T2_FIRST_IN_JOB = 1, T2_LAST_IN_JOB = 2, T2_FIRST_IN_CHUNK = 4, T2_LAST_IN_CHUNK = 8 };
+
+struct T2Op {                 // 16 bytes
+    uint32_t da;              // d_col | a_col << 16        (TMEM columns; the CTA owns all 512, base 0)
+    uint32_t b16;             // byte offset of the B image inside its ring slot, >> 4
+    uint32_t sbo_nk;          // (SBO >> 4) | nk << 16      (SBO = 8-row group pitch of the canonical K-major image)
+    uint32_t idesc;           // tcgen05 instruction descriptor; bit 0 = accumulate onto D from the first K step
+};
+struct T2Seg {                // maximal run of ops of one job reading one weight chunk; 14 bytes
+    uint16_t op_ofs[kTcIssuers + 1];   // ops of issuer q: [op_ofs[q], op_ofs[q+1])
+    uint8_t job, flags;
+    uint16_t pad;
+};
+struct T2Hidden { uint16_t col0, ncols, bias_off, pad; };
+struct T2Stage {
+    uint16_t seg_begin, seg_end, fin_begin, fin_end, chunk_begin, chunk_end;
+    T2Hidden hid[3];
+};
+struct T2Fin { uint16_t s_col, t_col, x_col, bs_off, bt_off; };   // bias offsets relative to the first bias float
+struct T2Chunk { uint32_t g_off16, bytes; };                      // offset in the packed buffer (16-byte units), size
+struct T2Prog {
+    int nstages, nfins, d, dc, xw, xc, xr;
+    int slot_bytes, n_slots, n_bias, bias_base;
+    int smem_tab, smem_bias, smem_in, smem_in_bytes, smem_out, smem_ring;   // byte offsets in dynamic shared memory
+    float alpha;
+    int round_acts;
+    T2Stage stages[kT2MaxStages];
+    T2Seg segs[kT2MaxSegs];
+    T2Op ops[kT2MaxOps];
+    T2Fin fins[kT2MaxFins];
+    T2Chunk chunks[kT2MaxChunks];
+    int16_t xlog[kT2MaxXw];
+};
+static_assert(sizeof(T2Prog) <= 32000, "the program must fit the 32 KB kernel-parameter space");
+
+struct T2Host {
+    bool ok = false;
+    std::string why;
+    size_t smem_bytes = 0;
+    T2Prog prog;
+};
+void build_tc2_program(const Plan& p, const TcSchedule& t, T2Host& out);
 
 inline int round8(int v) { return (v + 7) & ~7; }
 

@@ -28,3 +28,19 @@ def test_tc_program_matches_reference(golden):
     rc, zt, Jt, _ = emul_tc_lib.run(*args, tf32=True)
     tol = 2e-5 if golden["meta"]["init"] == "randn0.005" else 5e-3   # the stated TF32 bound (tests/test_gpu_tf32.py)
     assert rc == 0 and _err(zt, golden["z64"]) < tol and _err(Jt, golden["J64"]) < tol
+
+
+def test_tc2_program_matches_reference(golden):
+    """The v2 encoding (kernel-parameter program, ops partitioned per issuing warp, segments per job / weight chunk)."""
+    pk = plan_kwargs(golden["meta"])
+    args = (pk["d"], pk["dc"], pk["c_internal"], pk["clamp"], pk["max_splits"], pk["min_split_size"], golden["params"], golden["x"],
+            golden.get("c"))
+    rc, z, J, info = emul_tc_lib.run(*args, v2=True)
+    if rc == 200:
+        assert golden["meta"]["name"] == "wide_h_d12"
+        return
+    assert rc == 0
+    assert info[1] <= 227 * 1024 and info[2] >= 2 and info[3] <= 32000
+    assert _err(z, golden["z64"]) < 2e-5 and _err(J, golden["J64"]) < 2e-5
+    rc, xi, Ji, _ = emul_tc_lib.run(*args, rev=True, v2=True)
+    assert rc == 0 and _err(xi, golden["xinv64"]) < 2e-5 and _err(Ji, golden["Jinv64"]) < 2e-5
