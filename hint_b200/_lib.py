@@ -10,13 +10,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhint_b200.so")
 
 HINT_OK, HINT_ERR_INVALID, HINT_ERR_UNSUPPORTED, HINT_ERR_CUDA, HINT_ERR_WORKSPACE = 0, 1, 2, 3, 4
-MODE_FP32, MODE_TF32, MODE_TF32X3 = 0, 1, 2
+MODE_FP32, MODE_TF32, MODE_TF32X3, MODE_TF32_TCGEN05 = 0, 1, 2, 3
 WS_FORWARD, WS_BACKWARD = 0, 1
 
 # every symbol include/hint_b200.h declares (tests/test_capi.py checks the header against this list)
 EXPORTS = [
     "hint_plan_create", "hint_plan_destroy", "hint_plan_num_nodes", "hint_plan_node", "hint_plan_param_count",
-    "hint_plan_param_layout", "hint_plan_flops_per_sample", "hint_plan_tile_rows", "hint_workspace_bytes",
+    "hint_plan_param_layout", "hint_plan_flops_per_sample", "hint_plan_tile_rows", "hint_plan_mode_supported",
+    "hint_workspace_bytes",
     "hint_forward", "hint_backward", "hint_last_error", "hint_version",
 ]
 
@@ -35,16 +36,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("HINT_B200_LIB")   # developer switch: load a differently-built library (kernel experiments)
     try:
         from . import build as _build
-        if _build.is_stale():
+        if not override and _build.is_stale():
             _build.build()
     except Exception as e:  # no nvcc on this machine: fall through and require the prebuilt .so
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"hint_b200: native library {LIB_PATH} is missing and could not be built ({e}). "
                 "Run `python -m hint_b200.build` (needs nvcc, sm_100a). There is no fallback path.") from e
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(override or LIB_PATH)
     vp, i32, i64, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
     lib.hint_plan_create.restype = ctypes.c_int
     lib.hint_plan_create.argtypes = [i32, i32, ctypes.POINTER(i32), i32, ctypes.c_double, i32, i32, i32, ctypes.POINTER(vp)]
@@ -62,6 +64,8 @@ def load():
     lib.hint_plan_flops_per_sample.argtypes = [vp]
     lib.hint_plan_tile_rows.restype = i32
     lib.hint_plan_tile_rows.argtypes = [vp, i32]
+    lib.hint_plan_mode_supported.restype = i32
+    lib.hint_plan_mode_supported.argtypes = [vp, i32]
     lib.hint_workspace_bytes.restype = ctypes.c_size_t
     lib.hint_workspace_bytes.argtypes = [vp, i64, i32]
     lib.hint_forward.restype = ctypes.c_int

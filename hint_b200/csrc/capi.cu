@@ -12,6 +12,8 @@
 
 #include "plan.h"
 #include "plan_tc.h"
+#include "plan_mma.h"
+#include "mma_launch.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc2_kernels.cuh"
@@ -54,6 +56,7 @@ struct DevTc {
 struct DevPlan {
     DevSchedule fwd, bwd;
     DevTc tc;
+    DevMma mma;
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
     int num_sms = 0;
@@ -63,6 +66,7 @@ struct DevPlan {
 
 struct hint_plan {
     Plan p;
+    MmaPlan mma;
     TcSchedule tc;
     T2Host tc2;
     std::mutex mu;
@@ -127,6 +131,9 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     CUDA_TRY(setup_schedule(hp->p.bwd, true, d.num_sms, d.bwd));
     CUDA_TRY(upload(&d.pack_src, hp->p.pack_src));
     CUDA_TRY(upload(&d.unpack_src, hp->p.unpack_src));
+    if (hp->mma.ok) {
+        CUDA_TRY(mma_setup(hp->mma, d.num_sms, d.mma));
+    }
     if (hp->tc.ok) {
         CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
         CUDA_TRY(upload(&d.tc.ops, hp->tc.ops));
@@ -173,6 +180,14 @@ long long bwd_ctas(const Plan& p, const DevPlan& d, long long B) {
     return std::min<long long>(ntiles, d.bwd.max_ctas);
 }
 
+long long mma_bwd_ctas(const MmaPlan& m, const DevPlan& d, long long B) {
+    const long long ntiles = (B + m.bwd.TM - 1) / m.bwd.TM;
+    return std::min<long long>(ntiles, d.mma.bwd.max_ctas);
+}
+
+// packed operands of the warp-MMA path: [hi | lo], each n_packed floats (256-byte aligned)
+size_t mma_packed_bytes(const MmaPlan& m) { return 2 * align256((size_t)m.n_packed * 4); }
+
 }  // namespace
 
 extern "C" {
@@ -191,6 +206,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
         delete hp;
         return fail(code, err);
     }
+    build_mma_plan(hp->p, hp->mma);
     build_tc_schedule(hp->p, hp->tc);
     build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
@@ -208,6 +224,7 @@ void hint_plan_destroy(hint_plan_t* hp) {
             cudaFree(s->cgs); cudaFree(s->eps); cudaFree(s->dwjobs); cudaFree(s->stages);
         }
         cudaFree(d.pack_src); cudaFree(d.unpack_src);
+        mma_free(d.mma);
         cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
@@ -238,15 +255,27 @@ int32_t hint_plan_tile_rows(const hint_plan_t* hp, int32_t which) {
     return which == HINT_WS_BACKWARD ? hp->p.bwd.TM : hp->p.fwd.TM;
 }
 
+int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
+    if (!hp) return 0;
+    switch (mode) {
+        case HINT_MODE_FP32: return 1;
+        case HINT_MODE_TF32: case HINT_MODE_TF32X3: return hp->mma.ok ? 1 : 0;
+        case HINT_MODE_TF32_TCGEN05: return hp->tc.ok ? 1 : 0;
+    }
+    return 0;
+}
+
 size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
     if (!hp || B < 0) { fail(HINT_ERR_INVALID, "bad plan or batch"); return 0; }
     size_t bytes = align256((size_t)std::max<long long>(hp->p.n_packed, hp->tc.ok ? hp->tc.n_packed : 0) * 4);
+    if (hp->mma.ok) bytes = std::max(bytes, mma_packed_bytes(hp->mma));
     if (which == HINT_WS_BACKWARD) {
-        bytes = align256((size_t)hp->p.n_packed * 4);
         DevPlan* d = nullptr;
         if (get_dev(hp, &d) != HINT_OK) return 0;
-        bytes += align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
+        size_t part = align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
+        if (hp->mma.ok) part = std::max(part, align256((size_t)mma_bwd_ctas(hp->mma, *d, B) * (size_t)hp->mma.n_partial * 4));
+        bytes += part;
     }
     return bytes + 256;
 }
@@ -254,9 +283,11 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
 static int check_common(const hint_plan* hp, const float* x, const float* c, const float* params, int64_t B, int32_t mode) {
     if (!hp) return fail(HINT_ERR_INVALID, "plan is NULL");
     if (B < 0) return fail(HINT_ERR_INVALID, "negative batch");
-    if (mode == HINT_MODE_TF32X3) return fail(HINT_ERR_UNSUPPORTED, "HINT_MODE_TF32X3 is not built yet");
-    if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32) return fail(HINT_ERR_INVALID, "unknown mode");
-    if (mode == HINT_MODE_TF32 && !hp->tc.ok)
+    if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32 && mode != HINT_MODE_TF32X3 && mode != HINT_MODE_TF32_TCGEN05)
+        return fail(HINT_ERR_INVALID, "unknown mode");
+    if ((mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3) && !hp->mma.ok)
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the warp-MMA kernels' envelope: " + hp->mma.why);
+    if (mode == HINT_MODE_TF32_TCGEN05 && !hp->tc.ok)
         return fail(HINT_ERR_UNSUPPORTED, "this block is outside the TF32 (tcgen05) kernel's envelope: " + hp->tc.why);
     if (B > 0 && (!x || !params)) return fail(HINT_ERR_INVALID, "NULL input pointer");
     if (B > 0 && hp->p.dc > 0 && !c) return fail(HINT_ERR_INVALID, "plan has a condition input but c is NULL");
@@ -279,7 +310,16 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         return fail(HINT_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* packed = reinterpret_cast<float*>(workspace);
-    if (mode == HINT_MODE_TF32) {
+    if (mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3) {
+        const bool x3 = mode == HINT_MODE_TF32X3;
+        const MSchedule& s = hp->mma.fwd;
+        float* hi = packed;
+        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->mma.n_packed * 4));
+        CUDA_TRY(mma_pack(hp->mma, d->mma, params, hi, x3 ? lo : nullptr, st));
+        CUDA_TRY(mma_launch_fwd(hp->p, hp->mma, d->mma, x3, x, c, hi, lo, z, logdet, (long long)B, rev ? 1 : 0, st));
+        return HINT_OK;
+    }
+    if (mode == HINT_MODE_TF32_TCGEN05) {
         const TcSchedule& t = hp->tc;
         {
             const int threads = 256;
@@ -369,9 +409,9 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
                   const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
                   void* workspace, size_t workspace_bytes, void* stream) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
-    // The backward sweep currently always runs the FP32 CUDA-core kernel (also in TF32 mode, where it
-    // differentiates the exact function at the TF32-computed output).
-    int rc = check_common(hp, z, c, params, B, mode == HINT_MODE_TF32 ? HINT_MODE_FP32 : mode);
+    // HINT_MODE_TF32_TCGEN05 has no backward kernel of its own: it runs the FP32 CUDA-core sweep (which differentiates
+    // the exact function at the TF32-computed output).
+    int rc = check_common(hp, z, c, params, B, mode == HINT_MODE_TF32_TCGEN05 ? HINT_MODE_FP32 : mode);
     if (rc != HINT_OK) return rc;
     if (!dparams) return fail(HINT_ERR_INVALID, "dparams is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -387,6 +427,23 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
     if (!workspace || workspace_bytes < hint_workspace_bytes(hp, B, HINT_WS_BACKWARD))
         return fail(HINT_ERR_WORKSPACE, "workspace too small");
     float* packed = reinterpret_cast<float*>(workspace);
+    if (mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3) {
+        const bool x3 = mode == HINT_MODE_TF32X3;
+        const MSchedule& s = hp->mma.bwd;
+        float* hi = packed;
+        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->mma.n_packed * 4));
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mma_packed_bytes(hp->mma));
+        CUDA_TRY(mma_pack(hp->mma, d->mma, params, hi, x3 ? lo : nullptr, st));
+        const int grid = (int)mma_bwd_ctas(hp->mma, *d, B);
+        const long long np = hp->mma.n_partial;
+        CUDA_TRY(mma_launch_bwd(hp->p, hp->mma, d->mma, x3, grid, z, c, hi, lo, dz, dlogdet, x_rec, dx, dc, partials, (long long)B, st));
+        const long long n = hp->p.n_params;
+        const int threads = 256;
+        const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->mma.unpack_src, partials, grid, np, dparams, n);
+        CUDA_TRY(cudaGetLastError());
+        return HINT_OK;
+    }
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->p.n_packed * 4));
     if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
     const Schedule& s = hp->p.bwd;

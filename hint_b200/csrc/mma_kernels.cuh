@@ -1,0 +1,724 @@
+// Warp-MMA fused-tree kernels (HINT_MODE_TF32 / HINT_MODE_TF32X3): forward / inverse transport + log-det and the
+// memory-free backward of one HINT coupling block, subnet GEMMs on mma.sync.m16n8k8 tf32 with fp32 accumulation.
+//   forward / inverse : hint.py:62-101      backward : the autograd tape of the same lines (SURVEY 8a formulas)
+// Schedule, layouts and the reason this path exists next to the tcgen05 one: plan_mma.h.
+//
+// The code is written against four primitives (CTA barrier, warp MMA, read-only load, lane id) so that the very same
+// functions run under tests/emul/emul_mma.cpp, where a CTA is 256 fibers and mma_tf32 is a lane-exchange that
+// truncates its operands to 10 mantissa bits like the tensor core does.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "plan_mma.h"
+
+#if defined(__CUDACC__)
+#define HINT_DEV __device__ __forceinline__
+#define HINT_DEV_CALL __device__ __noinline__   // real calls: each task shape gets its own register allocation
+#else
+#define HINT_DEV_CALL inline
+#include <cmath>
+#define HINT_DEV inline
+namespace hint { namespace emu {
+void cta_sync();
+void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+} }
+#ifndef __restrict__
+#define __restrict__
+#endif
+#endif
+
+namespace hint {
+
+struct MmaTables {
+    const WOp* prog;            // op streams (plan_mma.h)
+    const Ep* eps;
+    int begin[kMmaWarps];       // first op of each warp's stream for this launch (forward / inverse / backward program)
+    int d, dc;
+    int col_x, col_d, col_one, col_zero;
+    int raw_off;
+    float alpha;
+};
+
+// ---- primitives ----------------------------------------------------------------------------------------------------
+HINT_DEV void m_cta_sync() {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#elif !defined(__CUDACC__)
+    emu::cta_sync();
+#endif
+}
+
+HINT_DEV void m_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#elif !defined(__CUDACC__)
+    emu::mma_tf32(c, a, b0, b1);
+#endif
+}
+
+HINT_DEV uint32_t m_bits(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(v);
+#else
+    uint32_t u; std::memcpy(&u, &v, 4); return u;
+#endif
+}
+HINT_DEV float m_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float v; std::memcpy(&v, &u, 4); return v;
+#endif
+}
+// round to nearest (ties away from zero) to tf32: the tensor core ignores the low 13 mantissa bits, so adding half an
+// ulp of the 10-bit mantissa to the magnitude is all the rounding needs (cvt.rna.tf32 runs at 16 lanes/clk/SM)
+HINT_DEV uint32_t m_rna(float v) { return m_bits(v) + 0x1000u; }
+HINT_DEV float m_trunc_tf32(uint32_t u) { return m_float(u & 0xFFFFE000u); }
+
+HINT_DEV void m_ld2(const float* __restrict__ p, float& a, float& b) {
+#if defined(__CUDA_ARCH__)
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+// B fragments stream from L2 and are read once per task: do not let them evict the op records from L1
+#ifndef HINT_MMA_EXP
+#define HINT_MMA_EXP 0
+#endif
+HINT_DEV void m_ld2_stream(const float* __restrict__ p, float& a, float& b) {
+#if defined(__CUDA_ARCH__) && (HINT_MMA_EXP & 2)
+    a = 0.01f; b = -0.01f;
+#elif defined(__CUDA_ARCH__) && (HINT_MMA_EXP & 1)
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    a = v.x; b = v.y;
+#elif defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+// partial[0..1] += {a, b}: fire-and-forget reduction at L2 (the address is owned by this thread: order = program order)
+HINT_DEV void m_red2(float* p, float a, float b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+#else
+    p[0] += a; p[1] += b;
+#endif
+}
+// exp / atan of the soft clamp (hint.py:56-60).  exp through ex2 (|x| <= clamp*0.636*pi/2: relative error ~2e-7);
+// atan by reciprocal range reduction + degree-7 minimax polynomial in x^2 (max abs error 1.7e-7).
+HINT_DEV float m_exp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+#else
+    return exp2f(x * 1.4426950408889634f);
+#endif
+}
+HINT_DEV float m_rcp(float a) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
+    return 1.f / a;
+#endif
+}
+HINT_DEV float m_atan(float x) {
+    const float a = fabsf(x);
+    const bool inv = a > 1.f;
+    const float r = inv ? m_rcp(a) : a;
+    const float t = r * r;
+    float p = -0.004780583083629608f;
+    p = fmaf(p, t, 0.024557599797844887f);
+    p = fmaf(p, t, -0.05990542098879814f);
+    p = fmaf(p, t, 0.09942812472581863f);
+    p = fmaf(p, t, -0.1402944177389145f);
+    p = fmaf(p, t, 0.199713796377182f);
+    p = fmaf(p, t, -0.3333209455013275f);
+    p = fmaf(p, t, 0.9999999403953552f);
+    float y = p * r;
+    if (inv) y = 1.5707963267948966f - y;
+    return copysignf(y, x);
+}
+
+// Operand packing (pack_src encoding: s >= 0 weight params[s], rounded to tf32; s == -1 zero; s <= -2 bias params[-s-2],
+// kept exact because it initialises the fp32 accumulator).  hi = rna_tf32(w), lo = rna_tf32(w - hi) (3xTF32 split).
+HINT_DEV void m_pack_elem(int s, const float* __restrict__ params, float& hi, float& lo) {
+    lo = 0.f;
+    if (s == -1) { hi = 0.f; return; }
+    if (s <= -2) { hi = params[-s - 2]; return; }
+    const float w = params[s];
+    hi = m_trunc_tf32(m_rna(w));
+    lo = m_trunc_tf32(m_rna(w - hi));
+}
+
+// round-to-nearest (ties away) to tf32 as a float (what the TF32 mode stores for every activation that is a GEMM operand,
+// so operand loads need no conversion)
+HINT_DEV float m_round_tf32(float v) { return m_trunc_tf32(m_rna(v)); }
+
+// ---- op records decoded into registers -------------------------------------------------------------------------------
+struct GemmOp { int w_off, b_off, ks_stride, ksteps, in_off, k0, in1_off, k1, out_off, zero_off, nvalid, flags; };
+struct DwOp { int out_off, a_off, N, n0, kf0, in_off, k0, in1_off, k1, ld, nstore, one_off, zero_off; };
+HINT_DEV int m_lo16(int w) { return w & 0xffff; }
+HINT_DEV int m_hi16(int w) { return (int)((unsigned)w >> 16); }
+HINT_DEV GemmOp m_decode_gemm(const int (&r)[8]) {
+    GemmOp o;
+    o.w_off = r[0]; o.b_off = r[1];
+    o.ks_stride = m_lo16(r[2]); o.ksteps = m_hi16(r[2]);
+    o.in_off = m_lo16(r[3]); o.k0 = m_hi16(r[3]);
+    o.in1_off = m_lo16(r[4]); o.k1 = m_hi16(r[4]);
+    o.out_off = m_lo16(r[5]); o.zero_off = m_hi16(r[5]);
+    o.nvalid = m_lo16(r[6]);
+    o.flags = r[7] & 0xff;
+    return o;
+}
+HINT_DEV DwOp m_decode_dw(const int (&r)[8]) {
+    DwOp o;
+    o.out_off = r[0];
+    o.a_off = m_lo16(r[1]); o.N = m_hi16(r[1]);
+    o.n0 = m_lo16(r[2]); o.kf0 = m_hi16(r[2]);
+    o.in_off = m_lo16(r[3]); o.k0 = m_hi16(r[3]);
+    o.in1_off = m_lo16(r[4]); o.k1 = m_hi16(r[4]);
+    o.ld = m_lo16(r[5]); o.nstore = m_hi16(r[5]);
+    o.one_off = m_lo16(r[6]); o.zero_off = m_hi16(r[6]);
+    return o;
+}
+HINT_DEV int m_op_type(const int (&r)[8]) { return (int)((unsigned)r[7] >> 24); }
+HINT_DEV int m_op_mt(const int (&r)[8], int word) { return (r[word] >> (word == 6 ? 16 : 0)) & 0xff; }
+HINT_DEV int m_op_nt(const int (&r)[8], int word) { return (r[word] >> (word == 6 ? 24 : 8)) & 0xff; }
+
+// ---- forward-type GEMM task ------------------------------------------------------------------------------------------
+// out[TM rows, 8*NT] (op)= in[TM rows, K] * B (+ bias).  A fragments from the column-major tile with the (2t, 2t+1) k-slot
+// permutation (conflict-free at pitch TM+4), B fragments streamed from the packed operand buffer kPF k-steps ahead (hi
+// parts in W, low parts in Wlo when X3).  FAST = one input segment of stored (already tf32-rounded) activations, K a
+// multiple of 8: pure pointer bumps, no conversion.  !FAST = layer 1: reads the exact x / condition columns, rounds on load.
+template <int TM, bool X3, int NT, bool FAST>
+HINT_DEV_CALL void m_gemm(int r0, int r1, int r2, int r3, int r4, int r5, int r6, int r7, float* S,
+                          const float* __restrict__ W, const float* __restrict__ Wlo, int lane) {
+    constexpr int TMS = TM + 4, MT = TM / 16;
+    const int rr[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    const GemmOp tk = m_decode_gemm(rr);
+    const int g = lane >> 2, t = lane & 3;
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float b0 = 0.f, b1 = 0.f;
+        if (tk.b_off >= 0) m_ld2(W + tk.b_off + 8 * j + 2 * t, b0, b1);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) { acc[i][j][0] = b0; acc[i][j][1] = b1; acc[i][j][2] = b0; acc[i][j][3] = b1; }
+    }
+    const float* wp = W + tk.w_off + 2 * lane;
+    const float* wl = X3 ? Wlo + tk.w_off + 2 * lane : nullptr;
+    float bq[kPF][NT][2], lq[X3 ? kPF : 1][NT][2];
+#pragma unroll
+    for (int s = 0; s < kPF; ++s) {
+        if (s < tk.ksteps) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                m_ld2_stream(wp + j * 64, bq[s][j][0], bq[s][j][1]);
+                if (X3) m_ld2_stream(wl + j * 64, lq[s][j][0], lq[s][j][1]);
+            }
+        }
+        wp += tk.ks_stride;
+        if (X3) wl += tk.ks_stride;
+    }
+    const int K = tk.k0 + tk.k1;
+    const float* pa = S + tk.in_off + 2 * t * TMS + g;
+    for (int ks = 0; ks < tk.ksteps; ++ks) {
+        const float* p0;
+        const float* p1;
+        if (FAST) {
+            p0 = pa; p1 = pa + TMS; pa += 8 * TMS;
+        } else {
+            const int f0 = 8 * ks + 2 * t, f1 = f0 + 1;
+            const int o0 = f0 < tk.k0 ? tk.in_off + f0 * TMS : (f0 < K ? tk.in1_off + (f0 - tk.k0) * TMS : tk.zero_off);
+            const int o1 = f1 < tk.k0 ? tk.in_off + f1 * TMS : (f1 < K ? tk.in1_off + (f1 - tk.k0) * TMS : tk.zero_off);
+            p0 = S + o0 + g; p1 = S + o1 + g;
+        }
+        uint32_t a[MT][4], al[X3 ? MT : 1][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const float v[4] = {p0[16 * i], p0[16 * i + 8], p1[16 * i], p1[16 * i + 8]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (X3) {
+                    a[i][e] = m_rna(v[e]);
+                    al[i][e] = m_rna(v[e] - m_trunc_tf32(a[i][e]));
+                } else {
+                    a[i][e] = FAST ? m_bits(v[e]) : m_rna(v[e]);   // FAST operands were rounded when they were stored
+                }
+            }
+        }
+        float b[NT][2], bl[X3 ? NT : 1][2];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            b[j][0] = bq[0][j][0]; b[j][1] = bq[0][j][1];
+            if (X3) { bl[j][0] = lq[0][j][0]; bl[j][1] = lq[0][j][1]; }
+#pragma unroll
+            for (int s = 0; s + 1 < kPF; ++s) {
+                bq[s][j][0] = bq[s + 1][j][0]; bq[s][j][1] = bq[s + 1][j][1];
+                if (X3) { lq[s][j][0] = lq[s + 1][j][0]; lq[s][j][1] = lq[s + 1][j][1]; }
+            }
+        }
+        if (ks + kPF < tk.ksteps) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                m_ld2_stream(wp + j * 64, bq[kPF - 1][j][0], bq[kPF - 1][j][1]);
+                if (X3) m_ld2_stream(wl + j * 64, lq[kPF - 1][j][0], lq[kPF - 1][j][1]);
+            }
+        }
+        wp += tk.ks_stride;
+        if (X3) wl += tk.ks_stride;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                if (X3) {
+                    m_mma(acc[i][j], al[i], m_bits(b[j][0]), m_bits(b[j][1]));
+                    m_mma(acc[i][j], a[i], m_bits(bl[j][0]), m_bits(bl[j][1]));
+                }
+                m_mma(acc[i][j], a[i], m_bits(b[j][0]), m_bits(b[j][1]));
+            }
+        }
+    }
+    // epilogue: C fragment (row g / g+8, col 2t / 2t+1) -> column-major tile; every offset below is a compile-time constant.
+    // Three straight-line variants chosen by a warp-uniform branch: write-only (bias+ReLU or plain), mask (dH = G * [h > 0],
+    // in place over h), accumulate (dx_upper += ...).  Stored GEMM operands are rounded to tf32 here (not in X3 mode).
+    float* q = S + tk.out_off + 2 * t * TMS + g;
+    const bool rnd = !X3 && (tk.flags & (MT_RELU | MT_MASK));
+    const uint32_t radd = rnd ? 0x1000u : 0u, rmask = rnd ? 0xFFFFE000u : 0xFFFFFFFFu;
+    if (!(tk.flags & (MT_MASK | MT_ACCUM))) {
+        const float lo = (tk.flags & MT_RELU) ? 0.f : -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (8 * j + 2 * t + c < tk.nvalid) {
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            q[(8 * j + c) * TMS + 16 * i + 8 * hh] = m_float((m_bits(fmaxf(acc[i][j][2 * hh + c], lo)) + radd) & rmask);
+                }
+    } else if (tk.flags & MT_MASK) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (8 * j + 2 * t + c < tk.nvalid) {
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float* o = q + (8 * j + c) * TMS + 16 * i + 8 * hh;
+                            const float v = *o > 0.f ? acc[i][j][2 * hh + c] : 0.f;
+                            *o = m_float((m_bits(v) + radd) & rmask);
+                        }
+                }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (8 * j + 2 * t + c < tk.nvalid) {
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) q[(8 * j + c) * TMS + 16 * i + 8 * hh] += acc[i][j][2 * hh + c];
+                }
+    }
+}
+
+// ---- weight-gradient task ----------------------------------------------------------------------------------------------
+// dW[rows n0.., in-features kf0..] (+)= sum over the tile's samples of dOut[sample][row] * In[sample][feature]
+// (M = out rows, N = in-features, K = samples).  Both operands come from the column-major tile; the partial buffer is
+// private to the CTA and each element is owned by exactly one thread -> store on the first tile, fire-and-forget red after.
+template <int TM, bool X3, int MT, int NT>
+HINT_DEV_CALL void m_dw(int r0, int r1, int r2, int r3, int r4, int r5, int r6, int r7, const float* S,
+                        float* __restrict__ partial, bool first, int lane) {
+    constexpr int TMS = TM + 4;
+    const int rr[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    const DwOp tk = m_decode_dw(rr);
+    const int g = lane >> 2, t = lane & 3;
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    const float* pa[MT][2];
+    const float* pb[NT];
+    const int K = tk.k0 + tk.k1;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r = tk.n0 + 16 * i + 8 * hh + g;
+            pa[i][hh] = S + (r < tk.N ? tk.a_off + r * TMS : tk.zero_off) + t;
+        }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int f = tk.kf0 + 8 * j + g;
+        const int off = f < tk.k0 ? tk.in_off + f * TMS : (f < K ? tk.in1_off + (f - tk.k0) * TMS : (f == K ? tk.one_off : tk.zero_off));
+        pb[j] = S + off + t;
+    }
+#pragma unroll 2
+    for (int s0 = 0; s0 < TM; s0 += 8) {
+        uint32_t a[MT][4], al[X3 ? MT : 1][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const float v[4] = {pa[i][0][s0], pa[i][1][s0], pa[i][0][s0 + 4], pa[i][1][s0 + 4]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (X3) {
+                    a[i][e] = m_rna(v[e]);
+                    al[i][e] = m_rna(v[e] - m_trunc_tf32(a[i][e]));
+                } else {
+                    a[i][e] = m_bits(v[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float v0 = pb[j][s0], v1 = pb[j][s0 + 4];
+            uint32_t b0 = m_bits(v0), b1 = m_bits(v1), l0 = 0, l1 = 0;
+            if (X3) {
+                b0 = m_rna(v0); b1 = m_rna(v1);
+                l0 = m_rna(v0 - m_trunc_tf32(b0)); l1 = m_rna(v1 - m_trunc_tf32(b1));
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                if (X3) {
+                    m_mma(acc[i][j], al[i], b0, b1);
+                    m_mma(acc[i][j], a[i], l0, l1);
+                }
+                m_mma(acc[i][j], a[i], b0, b1);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r = tk.n0 + 16 * i + 8 * hh + g;
+            if (r < tk.N) {
+                float* qr = partial + tk.out_off + r * tk.ld + tk.kf0 + 2 * t;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (tk.kf0 + 8 * j + 2 * t < tk.nstore) {   // nstore and ld are such that the pair stays inside the row
+                        const float v0 = acc[i][j][2 * hh], v1 = acc[i][j][2 * hh + 1];
+                        if (first) { qr[8 * j] = v0; qr[8 * j + 1] = v1; }
+                        else m_red2(qr + 8 * j, v0, v1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- tile I/O and coupling epilogues (thread -> sample mapping as in simt_phases.cuh, for kMmaThreads threads) --------
+template <int TM>
+HINT_DEV void m_load_tile(int tid, float* S, int col_base, const float* __restrict__ gsrc, long long row0, long long B, int width) {
+    constexpr int TMS = TM + 4;
+    if (width == 0) return;
+    const long long base = row0 * width;
+    const long long rows = (B - row0) < TM ? (B - row0) : TM;
+    const int nvalid = (int)(rows * width);
+    const int n = TM * width;
+    for (int i = tid * 4; i < n; i += kMmaThreads * 4) {
+        float v[4];
+        if (i + 3 < nvalid) {
+#if defined(__CUDA_ARCH__)
+            const float4 q = __ldg(reinterpret_cast<const float4*>(gsrc + base + i));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+#else
+            for (int e = 0; e < 4; ++e) v[e] = gsrc[base + i + e];
+#endif
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (i + e < nvalid) ? gsrc[base + i + e] : 0.f;
+        }
+        int m = i / width, j = i - m * width;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (i + e < n) S[(col_base + j) * TMS + m] = v[e];
+            if (++j == width) { j = 0; ++m; }
+        }
+    }
+}
+
+template <int TM>
+HINT_DEV void m_store_tile(int tid, const float* S, int col_base, float* __restrict__ gdst, long long row0, long long B, int width) {
+    constexpr int TMS = TM + 4;
+    if (width == 0) return;
+    const long long base = row0 * width;
+    const long long rows = (B - row0) < TM ? (B - row0) : TM;
+    const int nvalid = (int)(rows * width);
+    for (int i = tid * 4; i < nvalid; i += kMmaThreads * 4) {
+        float v[4];
+        int m = i / width, j = i - m * width;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = (i + e < nvalid) ? S[(col_base + j) * TMS + m] : 0.f;
+            if (++j == width) { j = 0; ++m; }
+        }
+        if (i + 3 < nvalid) {
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<float4*>(gdst + base + i) = make_float4(v[0], v[1], v[2], v[3]);
+#else
+            for (int e = 0; e < 4; ++e) gdst[base + i + e] = v[e];
+#endif
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i + e < nvalid) gdst[base + i + e] = v[e];
+        }
+    }
+}
+
+// hint.py:79-84.  forward: x_l <- e(s) x_l + t, J += alpha atan s;  inverse: x_l <- (x_l - t) / e(s), J -= alpha atan s
+template <int TM>
+HINT_DEV void m_coupling(int tid, float* S, const Ep* __restrict__ eps, int begin, int end, float alpha, int col_x,
+                         float* JP, bool rev) {
+    constexpr int TMS = TM + 4, NJG = kMmaThreads / TM;
+    const int m = tid % TM;
+    float jacc = 0.f;
+    for (int e = begin + tid / TM; e < end; e += NJG) {
+        const Ep ep = eps[(HINT_MMA_EXP & 4) ? begin : e];
+        const float s = S[ep.s_col * TMS + m];
+        const float t = S[ep.t_col * TMS + m];
+        const float la = alpha * m_atan(s);
+        float* xp = S + (col_x + ep.x_col) * TMS + m;
+        if (!rev) {
+            *xp = fmaf(m_exp(la), *xp, t);
+            jacc += la;
+        } else {
+            *xp = (*xp - t) * m_exp(-la);
+            jacc -= la;
+        }
+    }
+    JP[tid] += jacc;
+}
+
+// backward coupling: x_l' = (z_l - t)/e ; dt = dz_l ; ds = (dz_l (z_l - t) + dJ) alpha/(1+s^2) ; dx_l' = dz_l e
+template <int TM, bool ROUND>
+HINT_DEV void m_coupling_bwd(int tid, float* S, const Ep* __restrict__ eps, int begin, int end, float alpha, int col_x,
+                             int col_d, const float* DJ) {
+    constexpr int TMS = TM + 4, NJG = kMmaThreads / TM;
+    const int m = tid % TM;
+    const float dj = DJ[m];
+    for (int e = begin + tid / TM; e < end; e += NJG) {
+        const Ep ep = eps[e];
+        float* sp = S + ep.s_col * TMS + m;
+        float* tp = S + ep.t_col * TMS + m;
+        float* xp = S + (col_x + ep.x_col) * TMS + m;
+        float* dp = S + (col_d + ep.x_col) * TMS + m;
+        const float s = *sp, t = *tp;
+        const float la = alpha * m_atan(s);
+        const float zl = *xp, dzl = *dp;
+        const float r = zl - t;
+        *xp = r * m_exp(-la);
+        *dp = dzl * m_exp(la);
+        const float ds = (dzl * r + dj) * (alpha * m_rcp(fmaf(s, s, 1.f)));
+        *tp = ROUND ? m_round_tf32(dzl) : dzl;    // ds, dt are only ever GEMM operands (G3, dW3)
+        *sp = ROUND ? m_round_tf32(ds) : ds;
+    }
+}
+
+// T.begin[warp] without dynamically indexing the kernel-parameter array (which would force a local-memory copy)
+HINT_DEV int m_begin(const MmaTables& T, int warp) {
+    int b = T.begin[0];
+#pragma unroll
+    for (int w = 1; w < kMmaWarps; ++w) b = (warp == w) ? T.begin[w] : b;
+    return b;
+}
+
+// ---- one tile through the tree: the warp interprets its op stream (plan_mma.h), next record always prefetched ------------
+HINT_DEV void m_ld_op(const WOp* __restrict__ p, int (&r)[8]) {
+#if defined(__CUDA_ARCH__)
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(p)), q1 = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w; r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
+#else
+    for (int i = 0; i < 8; ++i) r[i] = p->w[i];
+#endif
+}
+
+#define HINT_R8(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]
+template <int TM, bool X3>
+HINT_DEV void m_gemm_dispatch(const int (&r)[8], float* S, const float* __restrict__ W, const float* __restrict__ Wlo, int lane) {
+    const int nt = m_op_nt(r, 6);
+    if (r[7] & MT_FAST) {
+        if (nt == 3) m_gemm<TM, X3, 3, true>(HINT_R8(r), S, W, Wlo, lane);
+        else if (nt == 2) m_gemm<TM, X3, 2, true>(HINT_R8(r), S, W, Wlo, lane);
+        else m_gemm<TM, X3, 1, true>(HINT_R8(r), S, W, Wlo, lane);
+    } else {
+        if (nt == 3) m_gemm<TM, X3, 3, false>(HINT_R8(r), S, W, Wlo, lane);
+        else if (nt == 2) m_gemm<TM, X3, 2, false>(HINT_R8(r), S, W, Wlo, lane);
+        else m_gemm<TM, X3, 1, false>(HINT_R8(r), S, W, Wlo, lane);
+    }
+}
+
+template <int TM, bool X3>
+HINT_DEV void m_dw_dispatch(const int (&r)[8], const float* S, float* __restrict__ partial, bool first, int lane) {
+    const int mt = m_op_mt(r, 7), nt = m_op_nt(r, 7);
+    if (mt == 2) {
+        if (nt == 4) m_dw<TM, X3, 2, 4>(HINT_R8(r), S, partial, first, lane);
+        else if (nt == 3) m_dw<TM, X3, 2, 3>(HINT_R8(r), S, partial, first, lane);
+        else if (nt == 2) m_dw<TM, X3, 2, 2>(HINT_R8(r), S, partial, first, lane);
+        else m_dw<TM, X3, 2, 1>(HINT_R8(r), S, partial, first, lane);
+    } else {
+        if (nt == 4) m_dw<TM, X3, 1, 4>(HINT_R8(r), S, partial, first, lane);
+        else if (nt == 3) m_dw<TM, X3, 1, 3>(HINT_R8(r), S, partial, first, lane);
+        else if (nt == 2) m_dw<TM, X3, 1, 2>(HINT_R8(r), S, partial, first, lane);
+        else m_dw<TM, X3, 1, 1>(HINT_R8(r), S, partial, first, lane);
+    }
+}
+
+// MODE 0 forward, 1 inverse, 2 backward
+template <int TM, bool X3, int MODE>
+HINT_DEV void m_run_program(const MmaTables& T, float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
+                            float* __restrict__ partial, bool first, int tid, int (&cur)[8]) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const WOp* pc = T.prog + m_begin(T, warp);
+    float* RAW = S + T.raw_off;
+    for (;;) {
+        const int type = m_op_type(cur);
+        if (type == OP_END) break;
+        ++pc;
+        int nxt[8];
+        m_ld_op(pc, nxt);
+        if (type == OP_GEMM) {
+            m_gemm_dispatch<TM, X3>(cur, S, W, Wlo, lane);
+        } else if (type == OP_DW) {
+            if (MODE == 2) m_dw_dispatch<TM, X3>(cur, S, partial, first, lane);
+        } else if (type == OP_SYNC) {
+            m_cta_sync();
+        } else if (type == OP_COUPLE) {
+            if (MODE == 2) m_coupling_bwd<TM, !X3>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, T.col_d, RAW);
+            else m_coupling<TM>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, RAW, MODE == 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+}
+
+template <int TM, bool X3>
+HINT_DEV void m_fwd_tile(const MmaTables& T, float* S, const float* __restrict__ x, const float* __restrict__ c,
+                         const float* __restrict__ W, const float* __restrict__ Wlo, float* __restrict__ z,
+                         float* __restrict__ logdet, long long B, int rev, long long row0, int tid) {
+    float* JP = S + T.raw_off;
+    int cur[8];
+    m_ld_op(T.prog + m_begin(T, tid >> 5), cur);
+    m_load_tile<TM>(tid, S, T.col_x, x, row0, B, T.d);
+    m_load_tile<TM>(tid, S, T.col_x + T.d, c, row0, B, T.dc);
+    JP[tid] = 0.f;
+    m_cta_sync();
+    if (rev) m_run_program<TM, X3, 1>(T, S, W, Wlo, nullptr, false, tid, cur);
+    else m_run_program<TM, X3, 0>(T, S, W, Wlo, nullptr, false, tid, cur);
+    m_store_tile<TM>(tid, S, T.col_x, z, row0, B, T.d);
+    if (tid < TM && row0 + tid < B) {
+        float j = 0.f;
+        for (int q = 0; q < kMmaThreads / TM; ++q) j += JP[q * TM + tid];
+        logdet[row0 + tid] = j;
+    }
+    m_cta_sync();
+}
+
+template <int TM, bool X3>
+HINT_DEV void m_bwd_tile(const MmaTables& T, float* S, const float* __restrict__ z, const float* __restrict__ c,
+                         const float* __restrict__ W, const float* __restrict__ Wlo, const float* __restrict__ dz,
+                         const float* __restrict__ dlogdet, float* __restrict__ x_rec, float* __restrict__ dx,
+                         float* __restrict__ dc, float* __restrict__ partial, bool first, long long B, long long row0, int tid) {
+    constexpr int TMS = TM + 4;
+    float* DJ = S + T.raw_off;
+    int cur[8];
+    m_ld_op(T.prog + m_begin(T, tid >> 5), cur);
+    m_load_tile<TM>(tid, S, T.col_x, z, row0, B, T.d);
+    m_load_tile<TM>(tid, S, T.col_x + T.d, c, row0, B, T.dc);
+    m_load_tile<TM>(tid, S, T.col_d, dz, row0, B, T.d);
+    for (int i = tid; i < T.dc * TM; i += kMmaThreads) S[(T.col_d + T.d + i / TM) * TMS + i % TM] = 0.f;
+    if (tid < TM) DJ[tid] = (row0 + tid < B) ? dlogdet[row0 + tid] : 0.f;
+    m_cta_sync();
+    m_run_program<TM, X3, 2>(T, S, W, Wlo, partial, first, tid, cur);
+    if (x_rec) m_store_tile<TM>(tid, S, T.col_x, x_rec, row0, B, T.d);
+    m_store_tile<TM>(tid, S, T.col_d, dx, row0, B, T.d);
+    if (dc) m_store_tile<TM>(tid, S, T.col_d + T.d, dc, row0, B, T.dc);
+    m_cta_sync();
+}
+
+template <int TM>
+HINT_DEV void m_init_consts(const MmaTables& T, float* S, int tid) {
+    constexpr int TMS = TM + 4;
+    for (int i = tid; i < TMS; i += kMmaThreads) {
+        S[T.col_one * TMS + i] = 1.f;
+        S[T.col_zero * TMS + i] = 0.f;
+    }
+}
+
+// whole-CTA bodies (persistent over tiles); `bid`/`nblocks` are blockIdx.x / gridDim.x
+template <int TM, bool X3>
+HINT_DEV void m_fwd_body(const MmaTables& T, float* S, const float* __restrict__ x, const float* __restrict__ c,
+                         const float* __restrict__ W, const float* __restrict__ Wlo, float* __restrict__ z,
+                         float* __restrict__ logdet, long long B, int rev, int tid, int bid, int nblocks) {
+    m_init_consts<TM>(T, S, tid);
+    const long long ntiles = (B + TM - 1) / TM;
+    for (long long tile = bid; tile < ntiles; tile += nblocks)
+        m_fwd_tile<TM, X3>(T, S, x, c, W, Wlo, z, logdet, B, rev, tile * TM, tid);
+}
+
+template <int TM, bool X3>
+HINT_DEV void m_bwd_body(const MmaTables& T, float* S, const float* __restrict__ z, const float* __restrict__ c,
+                         const float* __restrict__ W, const float* __restrict__ Wlo, const float* __restrict__ dz,
+                         const float* __restrict__ dlogdet, float* __restrict__ x_rec, float* __restrict__ dx,
+                         float* __restrict__ dc, float* __restrict__ partials, long long n_partial, long long B, int tid,
+                         int bid, int nblocks) {
+    m_init_consts<TM>(T, S, tid);
+    float* partial = partials + (long long)bid * n_partial;
+    const long long ntiles = (B + TM - 1) / TM;
+    bool first = true;
+    for (long long tile = bid; tile < ntiles; tile += nblocks) {
+        m_bwd_tile<TM, X3>(T, S, z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partial, first, B, tile * TM, tid);
+        first = false;
+    }
+}
+
+#if defined(__CUDACC__)
+template <int TM, bool X3>
+__global__ void __launch_bounds__(kMmaThreads, HINT_MMA_MINB)
+hint_fwd_mma_kernel(MmaTables T, const float* __restrict__ x, const float* __restrict__ c, const float* __restrict__ W,
+                    const float* __restrict__ Wlo, float* __restrict__ z, float* __restrict__ logdet, long long B, int rev) {
+    extern __shared__ float4 m_smem4[];
+    m_fwd_body<TM, X3>(T, reinterpret_cast<float*>(m_smem4), x, c, W, Wlo, z, logdet, B, rev, threadIdx.x, blockIdx.x, gridDim.x);
+}
+
+template <int TM, bool X3>
+__global__ void __launch_bounds__(kMmaThreads, HINT_MMA_MINB)
+hint_bwd_mma_kernel(MmaTables T, const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ W,
+                    const float* __restrict__ Wlo, const float* __restrict__ dz, const float* __restrict__ dlogdet,
+                    float* __restrict__ x_rec, float* __restrict__ dx, float* __restrict__ dc, float* __restrict__ partials,
+                    long long n_partial, long long B) {
+    extern __shared__ float4 m_smem4[];
+    m_bwd_body<TM, X3>(T, reinterpret_cast<float*>(m_smem4), z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partials, n_partial, B,
+                       threadIdx.x, blockIdx.x, gridDim.x);
+}
+
+__global__ void hint_pack_mma_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ hi,
+                                     float* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float h, l;
+        m_pack_elem(src[i], params, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace hint

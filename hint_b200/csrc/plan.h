@@ -114,6 +114,7 @@ std::string build_plan(Plan& p, int d, int dc, const int32_t* c_internal, int n_
                        int max_splits, int min_split_size, int reshuffle, int* code);
 
 inline int round4(int v) { return (v + 3) & ~3; }
+inline int round8(int v) { return (v + 7) & ~7; }
 inline int round16(int v) { return (v + 15) & ~15; }
 
 }  // namespace hint

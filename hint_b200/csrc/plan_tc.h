@@ -143,6 +143,4 @@ struct T2Host {
 };
 void build_tc2_program(const Plan& p, const TcSchedule& t, T2Host& out);
 
-inline int round8(int v) { return (v + 7) & ~7; }
-
 }  // namespace hint

@@ -36,8 +36,10 @@ extern "C" {
 
 /* arithmetic mode of the subnet GEMMs (accumulation is always fp32) */
 #define HINT_MODE_FP32 0        /* CUDA-core FFMA, bit-for-bit fp32 products                    */
-#define HINT_MODE_TF32 1        /* tcgen05 kind::tf32, operands rounded to 10-bit mantissa      */
-#define HINT_MODE_TF32X3 2      /* tcgen05 3xTF32 split (big*big + big*small + small*big)       */
+#define HINT_MODE_TF32 1        /* tensor cores, operands rounded to 10-bit mantissa (warp-MMA fused-tree kernels;
+                                   forward, inverse and backward)                                 */
+#define HINT_MODE_TF32X3 2      /* same kernels, 3xTF32 split (big*big + small*big + big*small): fp32-class accuracy */
+#define HINT_MODE_TF32_TCGEN05 3 /* tcgen05 kind::tf32 / TMEM forward+inverse kernel (backward runs the FP32 sweep)  */
 
 /* which workspace hint_workspace_bytes() sizes */
 #define HINT_WS_FORWARD 0
@@ -75,6 +77,9 @@ int hint_plan_param_layout(const hint_plan_t* plan, int64_t* offsets, int64_t n_
 int64_t hint_plan_flops_per_sample(const hint_plan_t* plan);
 /* samples per CTA tile chosen for the forward / backward schedule (for reporting) */
 int32_t hint_plan_tile_rows(const hint_plan_t* plan, int32_t which);
+
+/* 1 when `mode` can run this block (every kernel family has a shared-memory / TMEM envelope; FP32 is the widest) */
+int32_t hint_plan_mode_supported(const hint_plan_t* plan, int32_t mode);
 
 size_t hint_workspace_bytes(const hint_plan_t* plan, int64_t B, int32_t which);
 

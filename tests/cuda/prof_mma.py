@@ -1,0 +1,19 @@
+"""ncu driver: forward + backward of one d=43 hint_8-width block through the warp-MMA kernels.
+    python tests/cuda/prof_mma.py [B] [mode]"""
+import os
+import sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from hint_b200 import HierarchicalAffineCouplingBlock
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 2 * 64 * 4
+mode = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+blk = HierarchicalAffineCouplingBlock([(43,)], c_internal=[67, 33, 16, 8]).to(dev)
+x = torch.randn(B, 43, device=dev)
+with torch.no_grad():
+    for _ in range(2):
+        z, J = blk.plan.forward(x, None, blk.flat.detach(), mode=mode)
+        out = blk.plan.backward(z, None, blk.flat.detach(), z / B, torch.full((B,), -1.0 / B, device=dev), mode=mode)
+torch.cuda.synchronize()
+print("ok")
