@@ -324,7 +324,9 @@ def run_ours(args, w, name):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(name, {}).get("bwd_dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": f"hint_bwd_{args.mode}_kernel (one block, B={B})", "achieved": achieved,
+    kname = {"fp32": "hint_bwd_fp32_kernel", "tf32_tcgen05": "hint_bwd_fp32_kernel", "tf32x3": "hint_bwd_mma_kernel<TM,3xTF32>"}.get(
+        args.mode, "hint_bwd_mma_kernel<TM,TF32>")
+    roofline = {"bound": "tensor", "kernel": f"{kname} (one block, B={B})", "achieved": achieved,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
                 "peak_source": f"TF32 dense = bf16_tflops_sustained/2 of {peak_src}",
                 "flops_per_launch": 2 * Fb * B, "ms_per_launch": ms_b,
@@ -361,7 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d43_hint_8", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
-    ap.add_argument("--mode", default=os.environ.get("HINT_B200_MODE", "fp32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--mode", default=os.environ.get("HINT_B200_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3", "tf32_mma", "tf32_tcgen05"])
     ap.add_argument("--cpu-sample", type=int, default=32768, help="samples per CPU step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -191,52 +191,82 @@ HINT_DEV DwOp m_decode_dw(const int (&r)[8]) {
     return o;
 }
 HINT_DEV int m_op_type(const int (&r)[8]) { return (int)((unsigned)r[7] >> 24); }
-HINT_DEV int m_op_mt(const int (&r)[8], int word) { return (r[word] >> (word == 6 ? 16 : 0)) & 0xff; }
-HINT_DEV int m_op_nt(const int (&r)[8], int word) { return (r[word] >> (word == 6 ? 24 : 8)) & 0xff; }
+HINT_DEV int m_op_flags(const int (&r)[8]) { return r[7] & 0xff; }
+HINT_DEV int m_gemm_nt(const int (&r)[8]) { return (r[6] >> 24) & 0xff; }
+HINT_DEV int m_dw_mt(const int (&r)[8]) { return (r[7] >> 8) & 0xff; }
+HINT_DEV int m_dw_nt(const int (&r)[8]) { return (r[7] >> 16) & 0xff; }
+HINT_DEV void m_prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
 
 // ---- forward-type GEMM task ------------------------------------------------------------------------------------------
-// out[TM rows, 8*NT] (op)= in[TM rows, K] * B (+ bias).  A fragments from the column-major tile with the (2t, 2t+1) k-slot
-// permutation (conflict-free at pitch TM+4), B fragments streamed from the packed operand buffer kPF k-steps ahead (hi
-// parts in W, low parts in Wlo when X3).  FAST = one input segment of stored (already tf32-rounded) activations, K a
-// multiple of 8: pure pointer bumps, no conversion.  !FAST = layer 1: reads the exact x / condition columns, rounds on load.
-template <int TM, bool X3, int NT, bool FAST>
-HINT_DEV_CALL void m_gemm(int r0, int r1, int r2, int r3, int r4, int r5, int r6, int r7, float* S,
-                          const float* __restrict__ W, const float* __restrict__ Wlo, int lane) {
-    constexpr int TMS = TM + 4, MT = TM / 16;
-    const int rr[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
-    const GemmOp tk = m_decode_gemm(rr);
-    const int g = lane >> 2, t = lane & 3;
-    float acc[MT][NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        float b0 = 0.f, b1 = 0.f;
-        if (tk.b_off >= 0) m_ld2(W + tk.b_off + 8 * j + 2 * t, b0, b1);
-#pragma unroll
-        for (int i = 0; i < MT; ++i) { acc[i][j][0] = b0; acc[i][j][1] = b1; acc[i][j][2] = b0; acc[i][j][3] = b1; }
-    }
+// out[TM rows, 8*nt] (op)= in[TM rows, K] * B (+ bias).  A fragments from the column-major tile with the (2t, 2t+1) k-slot
+// permutation (conflict-free at pitch TM+4); B fragments stream from the packed operand buffer (hi parts in W, low parts
+// in Wlo when X3) through a register ring that always holds the next kPF k-steps.  The ring of a task is filled by
+// m_issue_b, which the interpreter calls as early as possible: right after the PREVIOUS task's k-loop (before its epilogue
+// and before the phase barrier), so the L2 latency of the first fragments is off the critical path.
+// MT_FAST = one input segment of stored (already tf32-rounded) activations, K a multiple of 8: pure pointer bumps, no
+// conversion.  Otherwise (layer 1) the task reads the exact x / condition columns and rounds on load.
+template <bool X3>
+struct BRing {
+    float b[kPF][kNC][2];
+    float l[X3 ? kPF : 1][kNC][2];
+    float bias[kNC][2];
+};
+
+template <bool X3>
+HINT_DEV void m_issue_b(const GemmOp& tk, int nt, const float* __restrict__ W, const float* __restrict__ Wlo, int lane,
+                        BRing<X3>& R) {
+    const int t = lane & 3;
     const float* wp = W + tk.w_off + 2 * lane;
     const float* wl = X3 ? Wlo + tk.w_off + 2 * lane : nullptr;
-    float bq[kPF][NT][2], lq[X3 ? kPF : 1][NT][2];
+#pragma unroll
+    for (int j = 0; j < kNC; ++j) {
+        R.bias[j][0] = 0.f; R.bias[j][1] = 0.f;
+        if (j < nt && tk.b_off >= 0) m_ld2(W + tk.b_off + 8 * j + 2 * t, R.bias[j][0], R.bias[j][1]);
+    }
 #pragma unroll
     for (int s = 0; s < kPF; ++s) {
         if (s < tk.ksteps) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                m_ld2_stream(wp + j * 64, bq[s][j][0], bq[s][j][1]);
-                if (X3) m_ld2_stream(wl + j * 64, lq[s][j][0], lq[s][j][1]);
+            for (int j = 0; j < kNC; ++j) {
+                if (j < nt) {
+                    m_ld2_stream(wp + j * 64, R.b[s][j][0], R.b[s][j][1]);
+                    if (X3) m_ld2_stream(wl + j * 64, R.l[s][j][0], R.l[s][j][1]);
+                }
             }
         }
         wp += tk.ks_stride;
         if (X3) wl += tk.ks_stride;
     }
+}
+
+// k-loop of one task; the ring holds k-steps [0, kPF) on entry and is dead on exit
+template <int TM, bool X3>
+HINT_DEV void m_gemm_kloop(const GemmOp& tk, int nt, const float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
+                           int lane, BRing<X3>& R, float (&acc)[TM / 16][kNC][4]) {
+    constexpr int TMS = TM + 4, MT = TM / 16;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < kNC; ++j)
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            acc[i][j][0] = R.bias[j][0]; acc[i][j][1] = R.bias[j][1]; acc[i][j][2] = R.bias[j][0]; acc[i][j][3] = R.bias[j][1];
+        }
+    const bool fast = tk.flags & MT_FAST;
+    const float* wp = W + tk.w_off + 2 * lane + kPF * tk.ks_stride;
+    const float* wl = X3 ? Wlo + tk.w_off + 2 * lane + kPF * tk.ks_stride : nullptr;
     const int K = tk.k0 + tk.k1;
     const float* pa = S + tk.in_off + 2 * t * TMS + g;
     for (int ks = 0; ks < tk.ksteps; ++ks) {
-        const float* p0;
-        const float* p1;
-        if (FAST) {
-            p0 = pa; p1 = pa + TMS; pa += 8 * TMS;
-        } else {
+        const float* p0 = pa;
+        const float* p1 = pa + TMS;
+        pa += 8 * TMS;
+        if (!fast) {
             const int f0 = 8 * ks + 2 * t, f1 = f0 + 1;
             const int o0 = f0 < tk.k0 ? tk.in_off + f0 * TMS : (f0 < K ? tk.in1_off + (f0 - tk.k0) * TMS : tk.zero_off);
             const int o1 = f1 < tk.k0 ? tk.in_off + f1 * TMS : (f1 < K ? tk.in1_off + (f1 - tk.k0) * TMS : tk.zero_off);
@@ -252,55 +282,71 @@ HINT_DEV_CALL void m_gemm(int r0, int r1, int r2, int r3, int r4, int r5, int r6
                     a[i][e] = m_rna(v[e]);
                     al[i][e] = m_rna(v[e] - m_trunc_tf32(a[i][e]));
                 } else {
-                    a[i][e] = FAST ? m_bits(v[e]) : m_rna(v[e]);   // FAST operands were rounded when they were stored
+                    a[i][e] = m_bits(v[e]);
                 }
             }
         }
-        float b[NT][2], bl[X3 ? NT : 1][2];
+        if (!X3 && !fast) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            b[j][0] = bq[0][j][0]; b[j][1] = bq[0][j][1];
-            if (X3) { bl[j][0] = lq[0][j][0]; bl[j][1] = lq[0][j][1]; }
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[i][e] += 0x1000u;
+        }
+        float b[kNC][2], bl[X3 ? kNC : 1][2];
+#pragma unroll
+        for (int j = 0; j < kNC; ++j) {
+            b[j][0] = R.b[0][j][0]; b[j][1] = R.b[0][j][1];
+            if (X3) { bl[j][0] = R.l[0][j][0]; bl[j][1] = R.l[0][j][1]; }
 #pragma unroll
             for (int s = 0; s + 1 < kPF; ++s) {
-                bq[s][j][0] = bq[s + 1][j][0]; bq[s][j][1] = bq[s + 1][j][1];
-                if (X3) { lq[s][j][0] = lq[s + 1][j][0]; lq[s][j][1] = lq[s + 1][j][1]; }
+                R.b[s][j][0] = R.b[s + 1][j][0]; R.b[s][j][1] = R.b[s + 1][j][1];
+                if (X3) { R.l[s][j][0] = R.l[s + 1][j][0]; R.l[s][j][1] = R.l[s + 1][j][1]; }
             }
         }
         if (ks + kPF < tk.ksteps) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                m_ld2_stream(wp + j * 64, bq[kPF - 1][j][0], bq[kPF - 1][j][1]);
-                if (X3) m_ld2_stream(wl + j * 64, lq[kPF - 1][j][0], lq[kPF - 1][j][1]);
+            for (int j = 0; j < kNC; ++j) {
+                if (j < nt) {
+                    m_ld2_stream(wp + j * 64, R.b[kPF - 1][j][0], R.b[kPF - 1][j][1]);
+                    if (X3) m_ld2_stream(wl + j * 64, R.l[kPF - 1][j][0], R.l[kPF - 1][j][1]);
+                }
             }
         }
         wp += tk.ks_stride;
         if (X3) wl += tk.ks_stride;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
+        for (int j = 0; j < kNC; ++j) {
+            if (j < nt) {
 #pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                if (X3) {
-                    m_mma(acc[i][j], al[i], m_bits(b[j][0]), m_bits(b[j][1]));
-                    m_mma(acc[i][j], a[i], m_bits(bl[j][0]), m_bits(bl[j][1]));
+                for (int i = 0; i < MT; ++i) {
+                    if (X3) {
+                        m_mma(acc[i][j], al[i], m_bits(b[j][0]), m_bits(b[j][1]));
+                        m_mma(acc[i][j], a[i], m_bits(bl[j][0]), m_bits(bl[j][1]));
+                    }
+                    m_mma(acc[i][j], a[i], m_bits(b[j][0]), m_bits(b[j][1]));
                 }
-                m_mma(acc[i][j], a[i], m_bits(b[j][0]), m_bits(b[j][1]));
             }
         }
     }
-    // epilogue: C fragment (row g / g+8, col 2t / 2t+1) -> column-major tile; every offset below is a compile-time constant.
-    // Three straight-line variants chosen by a warp-uniform branch: write-only (bias+ReLU or plain), mask (dH = G * [h > 0],
-    // in place over h), accumulate (dx_upper += ...).  Stored GEMM operands are rounded to tf32 here (not in X3 mode).
+}
+
+// epilogue: C fragment (row g / g+8, col 2t / 2t+1) -> column-major tile; every offset is a compile-time constant.
+// Three straight-line variants chosen by a warp-uniform branch: write-only (bias+ReLU or plain), mask (dH = G * [h > 0],
+// in place over h), accumulate (dx_upper += ...).  Stored GEMM operands are rounded to tf32 here (not in X3 mode).
+template <int TM, bool X3>
+HINT_DEV void m_gemm_epilogue(const GemmOp& tk, int nt, float* S, int lane, const float (&acc)[TM / 16][kNC][4]) {
+    constexpr int TMS = TM + 4, MT = TM / 16;
+    const int g = lane >> 2, t = lane & 3;
     float* q = S + tk.out_off + 2 * t * TMS + g;
     const bool rnd = !X3 && (tk.flags & (MT_RELU | MT_MASK));
     const uint32_t radd = rnd ? 0x1000u : 0u, rmask = rnd ? 0xFFFFE000u : 0xFFFFFFFFu;
     if (!(tk.flags & (MT_MASK | MT_ACCUM))) {
         const float lo = (tk.flags & MT_RELU) ? 0.f : -3.0e38f;
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+        for (int j = 0; j < kNC; ++j)
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-                if (8 * j + 2 * t + c < tk.nvalid) {
+                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -309,10 +355,10 @@ HINT_DEV_CALL void m_gemm(int r0, int r1, int r2, int r3, int r4, int r5, int r6
                 }
     } else if (tk.flags & MT_MASK) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+        for (int j = 0; j < kNC; ++j)
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-                if (8 * j + 2 * t + c < tk.nvalid) {
+                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -324,10 +370,10 @@ HINT_DEV_CALL void m_gemm(int r0, int r1, int r2, int r3, int r4, int r5, int r6
                 }
     } else {
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+        for (int j = 0; j < kNC; ++j)
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-                if (8 * j + 2 * t + c < tk.nvalid) {
+                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -553,22 +599,8 @@ HINT_DEV void m_ld_op(const WOp* __restrict__ p, int (&r)[8]) {
 
 #define HINT_R8(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]
 template <int TM, bool X3>
-HINT_DEV void m_gemm_dispatch(const int (&r)[8], float* S, const float* __restrict__ W, const float* __restrict__ Wlo, int lane) {
-    const int nt = m_op_nt(r, 6);
-    if (r[7] & MT_FAST) {
-        if (nt == 3) m_gemm<TM, X3, 3, true>(HINT_R8(r), S, W, Wlo, lane);
-        else if (nt == 2) m_gemm<TM, X3, 2, true>(HINT_R8(r), S, W, Wlo, lane);
-        else m_gemm<TM, X3, 1, true>(HINT_R8(r), S, W, Wlo, lane);
-    } else {
-        if (nt == 3) m_gemm<TM, X3, 3, false>(HINT_R8(r), S, W, Wlo, lane);
-        else if (nt == 2) m_gemm<TM, X3, 2, false>(HINT_R8(r), S, W, Wlo, lane);
-        else m_gemm<TM, X3, 1, false>(HINT_R8(r), S, W, Wlo, lane);
-    }
-}
-
-template <int TM, bool X3>
 HINT_DEV void m_dw_dispatch(const int (&r)[8], const float* S, float* __restrict__ partial, bool first, int lane) {
-    const int mt = m_op_mt(r, 7), nt = m_op_nt(r, 7);
+    const int mt = m_dw_mt(r), nt = m_dw_nt(r);
     if (mt == 2) {
         if (nt == 4) m_dw<TM, X3, 2, 4>(HINT_R8(r), S, partial, first, lane);
         else if (nt == 3) m_dw<TM, X3, 2, 3>(HINT_R8(r), S, partial, first, lane);
@@ -582,31 +614,49 @@ HINT_DEV void m_dw_dispatch(const int (&r)[8], const float* S, float* __restrict
     }
 }
 
-// MODE 0 forward, 1 inverse, 2 backward
-template <int TM, bool X3, int MODE>
+// The interpreter.  BWD selects the backward coupling and enables the weight-gradient ops; `rev` the inverse coupling.
+// `cur` holds the warp's first record (loaded by the caller before the tile load).
+template <int TM, bool X3, bool BWD>
 HINT_DEV void m_run_program(const MmaTables& T, float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
-                            float* __restrict__ partial, bool first, int tid, int (&cur)[8]) {
+                            float* __restrict__ partial, bool first, int tid, int rev, int (&cur)[8]) {
     const int warp = tid >> 5, lane = tid & 31;
     const WOp* pc = T.prog + m_begin(T, warp);
     float* RAW = S + T.raw_off;
+    BRing<X3> R;
+    bool ring_valid = false;   // R holds the first fragments of the next OP_GEMM
     for (;;) {
         const int type = m_op_type(cur);
         if (type == OP_END) break;
-        ++pc;
         int nxt[8];
-        m_ld_op(pc, nxt);
+        m_ld_op(pc + 1, nxt);
+        if (lane == 0) m_prefetch_l1(pc + 8);     // keep the op stream a few records ahead in L1
+        const bool sync = m_op_flags(cur) & MT_SYNC;
         if (type == OP_GEMM) {
-            m_gemm_dispatch<TM, X3>(cur, S, W, Wlo, lane);
-        } else if (type == OP_DW) {
-            if (MODE == 2) m_dw_dispatch<TM, X3>(cur, S, partial, first, lane);
-        } else if (type == OP_SYNC) {
-            m_cta_sync();
-        } else if (type == OP_COUPLE) {
-            if (MODE == 2) m_coupling_bwd<TM, !X3>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, T.col_d, RAW);
-            else m_coupling<TM>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, RAW, MODE == 1);
+            const GemmOp tk = m_decode_gemm(cur);
+            const int nt = m_gemm_nt(cur);
+            if (!ring_valid) m_issue_b<X3>(tk, nt, W, Wlo, lane, R);
+            if (sync) m_cta_sync();
+            float acc[TM / 16][kNC][4];
+            m_gemm_kloop<TM, X3>(tk, nt, S, W, Wlo, lane, R, acc);
+            ring_valid = m_op_type(nxt) == OP_GEMM;
+            if (ring_valid) m_issue_b<X3>(m_decode_gemm(nxt), m_gemm_nt(nxt), W, Wlo, lane, R);
+            m_gemm_epilogue<TM, X3>(tk, nt, S, lane, acc);
+        } else {
+            if (!ring_valid && m_op_type(nxt) == OP_GEMM) {
+                m_issue_b<X3>(m_decode_gemm(nxt), m_gemm_nt(nxt), W, Wlo, lane, R);
+                ring_valid = true;
+            }
+            if (sync || type == OP_SYNC) m_cta_sync();
+            if (type == OP_DW) {
+                if (BWD) m_dw_dispatch<TM, X3>(cur, S, partial, first, lane);
+            } else if (type == OP_COUPLE) {
+                if (BWD) m_coupling_bwd<TM, !X3>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, T.col_d, RAW);
+                else m_coupling<TM>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, RAW, rev != 0);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        ++pc;
     }
 }
 
@@ -621,8 +671,7 @@ HINT_DEV void m_fwd_tile(const MmaTables& T, float* S, const float* __restrict__
     m_load_tile<TM>(tid, S, T.col_x + T.d, c, row0, B, T.dc);
     JP[tid] = 0.f;
     m_cta_sync();
-    if (rev) m_run_program<TM, X3, 1>(T, S, W, Wlo, nullptr, false, tid, cur);
-    else m_run_program<TM, X3, 0>(T, S, W, Wlo, nullptr, false, tid, cur);
+    m_run_program<TM, X3, false>(T, S, W, Wlo, nullptr, false, tid, rev, cur);
     m_store_tile<TM>(tid, S, T.col_x, z, row0, B, T.d);
     if (tid < TM && row0 + tid < B) {
         float j = 0.f;
@@ -647,7 +696,7 @@ HINT_DEV void m_bwd_tile(const MmaTables& T, float* S, const float* __restrict__
     for (int i = tid; i < T.dc * TM; i += kMmaThreads) S[(T.col_d + T.d + i / TM) * TMS + i % TM] = 0.f;
     if (tid < TM) DJ[tid] = (row0 + tid < B) ? dlogdet[row0 + tid] : 0.f;
     m_cta_sync();
-    m_run_program<TM, X3, 2>(T, S, W, Wlo, partial, first, tid, cur);
+    m_run_program<TM, X3, true>(T, S, W, Wlo, partial, first, tid, 0, cur);
     if (x_rec) m_store_tile<TM>(tid, S, T.col_x, x_rec, row0, B, T.d);
     m_store_tile<TM>(tid, S, T.col_d, dx, row0, B, T.d);
     if (dc) m_store_tile<TM>(tid, S, T.col_d + T.d, dc, row0, B, T.dc);

@@ -363,13 +363,21 @@ std::string build_mschedule(const Plan& p, MmaPlan& m, const std::vector<NodeOps
         if (!bwd) for (int w = 0; w <= kMmaWarps; ++w) st.g_begin[w] = 0;
         s.stages.push_back(st);
     }
-    // linearise: one op stream per warp and direction
-    auto push = [&](const void* rec) { WOp o; std::memcpy(&o, rec, sizeof(o)); s.prog.push_back(o); };
-    auto push_ctl = [&](int type, int a, int b) { MTask t{}; t.type = (unsigned char)type; t.w_off = a; t.b_off = b; push(&t); };
+    // linearise: one op stream per warp and direction.  A phase boundary becomes the MT_SYNC flag of the warp's next op;
+    // boundaries with no op in between (the warp idles for a phase) and the final one become standalone OP_SYNC records.
     const int nprog = bwd ? 1 : 2;
     for (int pr = 0; pr < nprog; ++pr)
         for (int w = 0; w < kMmaWarps; ++w) {
             s.prog_begin[pr][w] = (int)s.prog.size();
+            int pending = 0;
+            auto push = [&](const void* rec) {
+                WOp o;
+                std::memcpy(&o, rec, sizeof(o));
+                for (; pending > 1; --pending) { MTask t{}; t.type = OP_SYNC; WOp so; std::memcpy(&so, &t, sizeof(so)); s.prog.push_back(so); }
+                if (pending == 1) { o.w[7] |= MT_SYNC; pending = 0; }   // flags live in the low byte of the last word of every record
+                s.prog.push_back(o);
+            };
+            auto push_ctl = [&](int type, int a, int b) { MTask t{}; t.type = (unsigned char)type; t.w_off = a; t.b_off = b; push(&t); };
             const int ns = (int)s.stages.size();
             for (int i = 0; i < ns; ++i) {
                 const MStage& st = s.stages[(bwd || pr == PROG_INV) ? i : ns - 1 - i];
@@ -379,11 +387,12 @@ std::string build_mschedule(const Plan& p, MmaPlan& m, const std::vector<NodeOps
                     if (dwp) for (int t = st.task_begin[ph][w]; t < st.task_begin[ph][w + 1]; ++t) push(&s.dtasks[t]);
                     if (ph == PH_DW1G1) for (int t = st.g_begin[w]; t < st.g_begin[w + 1]; ++t) push(&s.mtasks[t]);
                     if (!dwp) for (int t = st.task_begin[ph][w]; t < st.task_begin[ph][w + 1]; ++t) push(&s.mtasks[t]);
-                    push_ctl(OP_SYNC, 0, 0);
-                    if (ph == PH_L3) { push_ctl(OP_COUPLE, st.ep_begin, st.ep_end); push_ctl(OP_SYNC, 0, 0); }
+                    ++pending;
+                    if (ph == PH_L3) { push_ctl(OP_COUPLE, st.ep_begin, st.ep_end); ++pending; }
                 }
             }
-            push_ctl(OP_END, 0, 0);
+            for (; pending > 0; --pending) { MTask t{}; t.type = OP_SYNC; WOp so; std::memcpy(&so, &t, sizeof(so)); s.prog.push_back(so); }
+            for (int e = 0; e < 3; ++e) { MTask t{}; t.type = OP_END; WOp so; std::memcpy(&so, &t, sizeof(so)); s.prog.push_back(so); }   // look-ahead padding
         }
     s.ok = true;
     return "";

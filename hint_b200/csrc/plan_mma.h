@@ -30,10 +30,12 @@ constexpr int kPF = 3;    // k-steps of B fragments a forward-type task keeps in
 constexpr int kDMT = 2;   // max m-tiles (16 out-features each) of a weight-gradient task
 constexpr int kDNC = 4;   // max n-tiles (8 in-features each) of a weight-gradient task
 
-enum { MT_RELU = 1, MT_MASK = 2, MT_ACCUM = 4, MT_FAST = 8 };
+enum { MT_RELU = 1, MT_MASK = 2, MT_ACCUM = 4, MT_FAST = 8, MT_SYNC = 16 };   // MT_SYNC: CTA barrier before this op
 
 // A warp's PROGRAM for one tile is a linear stream of 32-byte op records that the kernel interprets with the next record
 // always prefetched.  All shared-memory positions are ELEMENT offsets (column * (TM+4)) so the kernel does no multiplies.
+// A phase boundary is the MT_SYNC flag of the warp's next op (or a standalone OP_SYNC when it has none in that phase): the
+// interpreter issues the next task's first weight fragments BEFORE that barrier, so L2 latency overlaps the wait.
 enum { OP_END = 0, OP_GEMM = 1, OP_DW = 2, OP_SYNC = 3, OP_COUPLE = 4 };
 
 // Forward-type task:  out[all TM rows] x [8*nt cols]  (op)=  in[rows x K] * B  (+ bias)
@@ -61,7 +63,7 @@ struct DTask {
     unsigned short in1_off, k1;
     unsigned short ld, nstore;            // in-features stored: columns < nstore
     unsigned short one_off, zero_off;
-    unsigned char mt, nt, pad, type;
+    unsigned char flags, mt, nt, type;    // flags: MT_SYNC
 };
 static_assert(sizeof(DTask) == 32, "op records are 32 bytes");
 

@@ -40,6 +40,8 @@ extern "C" {
                                    forward, inverse and backward)                                 */
 #define HINT_MODE_TF32X3 2      /* same kernels, 3xTF32 split (big*big + small*big + big*small): fp32-class accuracy */
 #define HINT_MODE_TF32_TCGEN05 3 /* tcgen05 kind::tf32 / TMEM forward+inverse kernel (backward runs the FP32 sweep)  */
+#define HINT_MODE_TF32_MMA 4    /* HINT_MODE_TF32 with the warp-MMA kernel forced for forward/inverse too (HINT_MODE_TF32
+                                   itself picks the faster of the two forward kernels the block fits)                */
 
 /* which workspace hint_workspace_bytes() sizes */
 #define HINT_WS_FORWARD 0
