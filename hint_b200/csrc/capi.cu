@@ -186,7 +186,8 @@ long long mma_bwd_ctas(const MmaPlan& m, const DevPlan& d, long long B) {
 }
 
 // packed operands of the warp-MMA path: [hi | lo], each n_packed floats (256-byte aligned)
-size_t mma_packed_bytes(const MmaPlan& m) { return 2 * align256((size_t)m.n_packed * 4); }
+size_t mma_half_bytes(const MmaPlan& m) { return align256((size_t)mma_copy_stride(m) * mma_weight_copies() * 4); }
+size_t mma_packed_bytes(const MmaPlan& m) { return 2 * mma_half_bytes(m); }
 
 }  // namespace
 
@@ -323,7 +324,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     if (mode == HINT_MODE_TF32_MMA || mode == HINT_MODE_TF32X3) {
         const bool x3 = mode == HINT_MODE_TF32X3;
         float* hi = packed;
-        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->mma.n_packed * 4));
+        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mma_half_bytes(hp->mma));
         CUDA_TRY(mma_pack(hp->mma, d->mma, params, hi, x3 ? lo : nullptr, st));
         CUDA_TRY(mma_launch_fwd(hp->p, hp->mma, d->mma, x3, x, c, hi, lo, z, logdet, (long long)B, rev ? 1 : 0, st));
         return HINT_OK;
@@ -439,7 +440,7 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
     if (mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3 || mode == HINT_MODE_TF32_MMA) {
         const bool x3 = mode == HINT_MODE_TF32X3;
         float* hi = packed;
-        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->mma.n_packed * 4));
+        float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mma_half_bytes(hp->mma));
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mma_packed_bytes(hp->mma));
         CUDA_TRY(mma_pack(hp->mma, d->mma, params, hi, x3 ? lo : nullptr, st));
         const int grid = (int)mma_bwd_ctas(hp->mma, *d, B);

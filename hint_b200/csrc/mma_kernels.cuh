@@ -28,19 +28,36 @@ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
 #endif
 #endif
 
+#ifndef HINT_MMA_EXP
+#define HINT_MMA_EXP 0   // developer experiments (timing only, wrong results): 2 no weight loads, 8 no MMA, 16 no A loads
+#endif
+
 namespace hint {
 
 struct MmaTables {
-    const WOp* prog;            // op streams (plan_mma.h)
+    const WOp* prog;            // op streams (plan_mma.h) in global memory ...
     const Ep* eps;
+    int in_param;               // ... or, when they fit, in the MmaParamProg kernel parameter (then `begin` indexes P.ops)
     int begin[kMmaWarps];       // first op of each warp's stream for this launch (forward / inverse / backward program)
     int d, dc;
     int col_x, col_d, col_one, col_zero;
     int raw_off;
     float alpha;
+    int wcopies;                // the packed operands are replicated `wcopies` times, `wstride` floats apart: CTA b reads copy
+    long long wstride;          // b % wcopies, so the 2*SMs CTAs running the same program do not hammer the same L2 lines
+    long long* dbg;             // optional: clock64 after every barrier of CTA 0's second tile ([0] = count) - HINT_B200_MMA_DEBUG
 };
 
 // ---- primitives ----------------------------------------------------------------------------------------------------
+HINT_DEV void m_dbg_stamp(long long* dbg, int tid, int bid) {
+#if defined(__CUDA_ARCH__)
+    if (dbg != nullptr && tid == 0 && bid == 0) {
+        const long long n = dbg[0];
+        if (n < 1000) { dbg[1 + n] = clock64(); dbg[0] = n + 1; }
+    }
+#endif
+}
+
 HINT_DEV void m_cta_sync() {
 #if defined(__CUDA_ARCH__)
     __syncthreads();
@@ -50,7 +67,9 @@ HINT_DEV void m_cta_sync() {
 }
 
 HINT_DEV void m_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && (HINT_MMA_EXP & 8)
+    c[0] += __uint_as_float(a[0]) * __uint_as_float(b0); c[3] += __uint_as_float(a[3]) * __uint_as_float(b1);
+#elif defined(__CUDA_ARCH__)
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -87,9 +106,6 @@ HINT_DEV void m_ld2(const float* __restrict__ p, float& a, float& b) {
 #endif
 }
 // B fragments stream from L2 and are read once per task: do not let them evict the op records from L1
-#ifndef HINT_MMA_EXP
-#define HINT_MMA_EXP 0
-#endif
 HINT_DEV void m_ld2_stream(const float* __restrict__ p, float& a, float& b) {
 #if defined(__CUDA_ARCH__) && (HINT_MMA_EXP & 2)
     a = 0.01f; b = -0.01f;
@@ -211,57 +227,95 @@ HINT_DEV void m_prefetch_l1(const void* p) {
 // and before the phase barrier), so the L2 latency of the first fragments is off the critical path.
 // MT_FAST = one input segment of stored (already tf32-rounded) activations, K a multiple of 8: pure pointer bumps, no
 // conversion.  Otherwise (layer 1) the task reads the exact x / condition columns and rounds on load.
-template <bool X3>
+template <bool X3, int PF>
 struct BRing {
-    float b[kPF][kNC][2];
-    float l[X3 ? kPF : 1][kNC][2];
+    float b[PF][kNC][2];
+    float l[X3 ? PF : 1][kNC][2];
     float bias[kNC][2];
 };
+// ring depth (k-steps of B fragments in flight): the accumulators of a TM = 32 tile need half the registers of a TM = 64 one
+template <int TM> struct RingDepth { static constexpr int value = TM >= 64 ? kPF : 2 * kPF; };
 
-template <bool X3>
-HINT_DEV void m_issue_b(const GemmOp& tk, int nt, const float* __restrict__ W, const float* __restrict__ Wlo, int lane,
-                        BRing<X3>& R) {
+template <bool X3, int NT, int PF>
+HINT_DEV void m_issue_b(const GemmOp& tk, const float* __restrict__ W, const float* __restrict__ Wlo, int lane, BRing<X3, PF>& R) {
     const int t = lane & 3;
     const float* wp = W + tk.w_off + 2 * lane;
     const float* wl = X3 ? Wlo + tk.w_off + 2 * lane : nullptr;
 #pragma unroll
-    for (int j = 0; j < kNC; ++j) {
+    for (int j = 0; j < NT; ++j) {
         R.bias[j][0] = 0.f; R.bias[j][1] = 0.f;
-        if (j < nt && tk.b_off >= 0) m_ld2(W + tk.b_off + 8 * j + 2 * t, R.bias[j][0], R.bias[j][1]);
+        if (tk.b_off >= 0) m_ld2(W + tk.b_off + 8 * j + 2 * t, R.bias[j][0], R.bias[j][1]);
     }
 #pragma unroll
-    for (int s = 0; s < kPF; ++s) {
+    for (int s = 0; s < PF; ++s) {
         if (s < tk.ksteps) {
 #pragma unroll
-            for (int j = 0; j < kNC; ++j) {
-                if (j < nt) {
-                    m_ld2_stream(wp + j * 64, R.b[s][j][0], R.b[s][j][1]);
-                    if (X3) m_ld2_stream(wl + j * 64, R.l[s][j][0], R.l[s][j][1]);
-                }
+            for (int j = 0; j < NT; ++j) {
+                m_ld2_stream(wp + j * 64, R.b[s][j][0], R.b[s][j][1]);
+                if (X3) m_ld2_stream(wl + j * 64, R.l[s][j][0], R.l[s][j][1]);
             }
         }
         wp += tk.ks_stride;
         if (X3) wl += tk.ks_stride;
     }
 }
+template <bool X3, int PF>
+HINT_DEV void m_issue_b_any(const int (&r)[8], const float* __restrict__ W, const float* __restrict__ Wlo, int lane, BRing<X3, PF>& R) {
+    const GemmOp tk = m_decode_gemm(r);
+    const int nt = m_gemm_nt(r);
+    if (nt == 3) m_issue_b<X3, 3, PF>(tk, W, Wlo, lane, R);
+    else if (nt == 2) m_issue_b<X3, 2, PF>(tk, W, Wlo, lane, R);
+    else m_issue_b<X3, 1, PF>(tk, W, Wlo, lane, R);
+}
+
+// Row <-> sample mapping of a forward-type task (TM = 64): MMA row (m-tile i, half hh, group g) is sample
+//   32*(jj/4) + 4*g + jj%4   with jj = 2*i + hh,
+// i.e. every lane owns two runs of 4 consecutive samples, so one column of A fragments (and one column of C fragments in
+// the epilogue) is two 128-bit shared-memory accesses instead of eight 32-bit ones; at pitch TM+4 the quarter-warps of those
+// accesses (g in {2q, 2q+1}, t in 0..3 -> word 8t + 4g) are bank-conflict free.  Samples are independent, so the mapping is
+// private to these two functions (the weight-gradient tasks contract over samples: any order).
+template <int TM>
+HINT_DEV void m_ld_col(const float* p, float (&v)[TM / 8]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int q = 0; q < TM / 32; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(p + 32 * q);
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+#else
+    for (int q = 0; q < TM / 32; ++q)
+        for (int e = 0; e < 4; ++e) v[4 * q + e] = p[32 * q + e];
+#endif
+}
+template <int TM>
+HINT_DEV void m_st_col(float* p, const float (&v)[TM / 8]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int q = 0; q < TM / 32; ++q) *reinterpret_cast<float4*>(p + 32 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#else
+    for (int q = 0; q < TM / 32; ++q)
+        for (int e = 0; e < 4; ++e) p[32 * q + e] = v[4 * q + e];
+#endif
+}
 
 // k-loop of one task; the ring holds k-steps [0, kPF) on entry and is dead on exit
-template <int TM, bool X3>
-HINT_DEV void m_gemm_kloop(const GemmOp& tk, int nt, const float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
-                           int lane, BRing<X3>& R, float (&acc)[TM / 16][kNC][4]) {
-    constexpr int TMS = TM + 4, MT = TM / 16;
+template <int TM, bool X3, int NT>
+HINT_DEV void m_gemm_kloop(const GemmOp& tk, const float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
+                           int lane, BRing<X3, RingDepth<TM>::value>& R, float (&acc)[TM / 16][kNC][4]) {
+    constexpr int TMS = TM + 4, MT = TM / 16, PF = RingDepth<TM>::value;
+    static_assert(TM % 32 == 0, "the vectorised row mapping needs whole runs of 32 samples");
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int j = 0; j < kNC; ++j)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
             acc[i][j][0] = R.bias[j][0]; acc[i][j][1] = R.bias[j][1]; acc[i][j][2] = R.bias[j][0]; acc[i][j][3] = R.bias[j][1];
         }
     const bool fast = tk.flags & MT_FAST;
-    const float* wp = W + tk.w_off + 2 * lane + kPF * tk.ks_stride;
-    const float* wl = X3 ? Wlo + tk.w_off + 2 * lane + kPF * tk.ks_stride : nullptr;
+    const float* wp = W + tk.w_off + 2 * lane + PF * tk.ks_stride;
+    const float* wl = X3 ? Wlo + tk.w_off + 2 * lane + PF * tk.ks_stride : nullptr;
     const int K = tk.k0 + tk.k1;
-    const float* pa = S + tk.in_off + 2 * t * TMS + g;
+    const float* pa = S + tk.in_off + 2 * t * TMS + 4 * g;
     for (int ks = 0; ks < tk.ksteps; ++ks) {
         const float* p0 = pa;
         const float* p1 = pa + TMS;
@@ -270,12 +324,15 @@ HINT_DEV void m_gemm_kloop(const GemmOp& tk, int nt, const float* S, const float
             const int f0 = 8 * ks + 2 * t, f1 = f0 + 1;
             const int o0 = f0 < tk.k0 ? tk.in_off + f0 * TMS : (f0 < K ? tk.in1_off + (f0 - tk.k0) * TMS : tk.zero_off);
             const int o1 = f1 < tk.k0 ? tk.in_off + f1 * TMS : (f1 < K ? tk.in1_off + (f1 - tk.k0) * TMS : tk.zero_off);
-            p0 = S + o0 + g; p1 = S + o1 + g;
+            p0 = S + o0 + 4 * g; p1 = S + o1 + 4 * g;
         }
+        float v0[TM / 8], v1[TM / 8];   // column 2t / 2t+1 of this k-step, the lane's 2*MT rows (jj = 2i + hh)
+        m_ld_col<TM>(p0, v0);
+        m_ld_col<TM>(p1, v1);
         uint32_t a[MT][4], al[X3 ? MT : 1][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-            const float v[4] = {p0[16 * i], p0[16 * i + 8], p1[16 * i], p1[16 * i + 8]};
+            const float v[4] = {v0[2 * i], v0[2 * i + 1], v1[2 * i], v1[2 * i + 1]};   // (g, 2t) (g+8, 2t) (g, 2t+1) (g+8, 2t+1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (X3) {
@@ -292,94 +349,100 @@ HINT_DEV void m_gemm_kloop(const GemmOp& tk, int nt, const float* S, const float
 #pragma unroll
                 for (int e = 0; e < 4; ++e) a[i][e] += 0x1000u;
         }
-        float b[kNC][2], bl[X3 ? kNC : 1][2];
+        float b[NT][2], bl[X3 ? NT : 1][2];
 #pragma unroll
-        for (int j = 0; j < kNC; ++j) {
+        for (int j = 0; j < NT; ++j) {
             b[j][0] = R.b[0][j][0]; b[j][1] = R.b[0][j][1];
             if (X3) { bl[j][0] = R.l[0][j][0]; bl[j][1] = R.l[0][j][1]; }
 #pragma unroll
-            for (int s = 0; s + 1 < kPF; ++s) {
+            for (int s = 0; s + 1 < PF; ++s) {
                 R.b[s][j][0] = R.b[s + 1][j][0]; R.b[s][j][1] = R.b[s + 1][j][1];
                 if (X3) { R.l[s][j][0] = R.l[s + 1][j][0]; R.l[s][j][1] = R.l[s + 1][j][1]; }
             }
         }
-        if (ks + kPF < tk.ksteps) {
+        if (ks + PF < tk.ksteps) {
 #pragma unroll
-            for (int j = 0; j < kNC; ++j) {
-                if (j < nt) {
-                    m_ld2_stream(wp + j * 64, R.b[kPF - 1][j][0], R.b[kPF - 1][j][1]);
-                    if (X3) m_ld2_stream(wl + j * 64, R.l[kPF - 1][j][0], R.l[kPF - 1][j][1]);
-                }
+            for (int j = 0; j < NT; ++j) {
+                m_ld2_stream(wp + j * 64, R.b[PF - 1][j][0], R.b[PF - 1][j][1]);
+                if (X3) m_ld2_stream(wl + j * 64, R.l[PF - 1][j][0], R.l[PF - 1][j][1]);
             }
         }
         wp += tk.ks_stride;
         if (X3) wl += tk.ks_stride;
 #pragma unroll
-        for (int j = 0; j < kNC; ++j) {
-            if (j < nt) {
+        for (int j = 0; j < NT; ++j) {
 #pragma unroll
-                for (int i = 0; i < MT; ++i) {
-                    if (X3) {
-                        m_mma(acc[i][j], al[i], m_bits(b[j][0]), m_bits(b[j][1]));
-                        m_mma(acc[i][j], a[i], m_bits(bl[j][0]), m_bits(bl[j][1]));
-                    }
-                    m_mma(acc[i][j], a[i], m_bits(b[j][0]), m_bits(b[j][1]));
+            for (int i = 0; i < MT; ++i) {
+                if (X3) {
+                    m_mma(acc[i][j], al[i], m_bits(b[j][0]), m_bits(b[j][1]));
+                    m_mma(acc[i][j], a[i], m_bits(bl[j][0]), m_bits(bl[j][1]));
                 }
+                m_mma(acc[i][j], a[i], m_bits(b[j][0]), m_bits(b[j][1]));
             }
         }
     }
 }
 
-// epilogue: C fragment (row g / g+8, col 2t / 2t+1) -> column-major tile; every offset is a compile-time constant.
+// epilogue: C fragment (row g / g+8, col 2t / 2t+1) -> column-major tile, one column of the lane's rows = two 128-bit stores.
 // Three straight-line variants chosen by a warp-uniform branch: write-only (bias+ReLU or plain), mask (dH = G * [h > 0],
 // in place over h), accumulate (dx_upper += ...).  Stored GEMM operands are rounded to tf32 here (not in X3 mode).
-template <int TM, bool X3>
-HINT_DEV void m_gemm_epilogue(const GemmOp& tk, int nt, float* S, int lane, const float (&acc)[TM / 16][kNC][4]) {
+template <int TM, bool X3, int NT>
+HINT_DEV void m_gemm_epilogue(const GemmOp& tk, float* S, int lane, const float (&acc)[TM / 16][kNC][4]) {
     constexpr int TMS = TM + 4, MT = TM / 16;
     const int g = lane >> 2, t = lane & 3;
-    float* q = S + tk.out_off + 2 * t * TMS + g;
+    float* q = S + tk.out_off + 2 * t * TMS + 4 * g;
     const bool rnd = !X3 && (tk.flags & (MT_RELU | MT_MASK));
     const uint32_t radd = rnd ? 0x1000u : 0u, rmask = rnd ? 0xFFFFE000u : 0xFFFFFFFFu;
-    if (!(tk.flags & (MT_MASK | MT_ACCUM))) {
-        const float lo = (tk.flags & MT_RELU) ? 0.f : -3.0e38f;
+    const int mode = (tk.flags & MT_MASK) ? 1 : ((tk.flags & MT_ACCUM) ? 2 : 0);
+    const float lo = (tk.flags & MT_RELU) ? 0.f : -3.0e38f;
 #pragma unroll
-        for (int j = 0; j < kNC; ++j)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
+        for (int c = 0; c < 2; ++c)
+            if (8 * j + 2 * t + c < tk.nvalid) {
+                float* o = q + (8 * j + c) * TMS;
+                float v[TM / 8];
 #pragma unroll
-                    for (int i = 0; i < MT; ++i)
+                for (int i = 0; i < MT; ++i) { v[2 * i] = acc[i][j][c]; v[2 * i + 1] = acc[i][j][2 + c]; }
+                if (mode == 0) {
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh)
-                            q[(8 * j + c) * TMS + 16 * i + 8 * hh] = m_float((m_bits(fmaxf(acc[i][j][2 * hh + c], lo)) + radd) & rmask);
+                    for (int e = 0; e < TM / 8; ++e) v[e] = m_float((m_bits(fmaxf(v[e], lo)) + radd) & rmask);
+                } else {
+                    float old[TM / 8];
+                    m_ld_col<TM>(o, old);
+                    if (mode == 1) {
+#pragma unroll
+                        for (int e = 0; e < TM / 8; ++e) v[e] = m_float((m_bits(old[e] > 0.f ? v[e] : 0.f) + radd) & rmask);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < TM / 8; ++e) v[e] += old[e];
+                    }
                 }
-    } else if (tk.flags & MT_MASK) {
-#pragma unroll
-        for (int j = 0; j < kNC; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
-#pragma unroll
-                    for (int i = 0; i < MT; ++i)
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            float* o = q + (8 * j + c) * TMS + 16 * i + 8 * hh;
-                            const float v = *o > 0.f ? acc[i][j][2 * hh + c] : 0.f;
-                            *o = m_float((m_bits(v) + radd) & rmask);
-                        }
-                }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kNC; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-                if (j < nt && 8 * j + 2 * t + c < tk.nvalid) {
-#pragma unroll
-                    for (int i = 0; i < MT; ++i)
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) q[(8 * j + c) * TMS + 16 * i + 8 * hh] += acc[i][j][2 * hh + c];
-                }
-    }
+                m_st_col<TM>(o, v);
+            }
+}
+
+template <int TM, bool X3, int NT>
+HINT_DEV void m_gemm_task(const int (&cur)[8], const int (&nxt)[8], bool sync, bool& ring_valid, float* S,
+                          const float* __restrict__ W, const float* __restrict__ Wlo, int lane, BRing<X3, RingDepth<TM>::value>& R,
+                          long long* dbg, int tid) {
+    const GemmOp tk = m_decode_gemm(cur);
+#if HINT_MMA_EXP & 32
+    m_dbg_stamp(dbg, tid, 0);
+#endif
+    if (!ring_valid) m_issue_b<X3, NT, RingDepth<TM>::value>(tk, W, Wlo, lane, R);
+    if (sync) { m_cta_sync(); m_dbg_stamp(dbg, tid, 0); }
+    float acc[TM / 16][kNC][4];
+    m_gemm_kloop<TM, X3, NT>(tk, S, W, Wlo, lane, R, acc);
+#if HINT_MMA_EXP & 32
+    m_dbg_stamp(dbg, tid, 0);
+#endif
+    ring_valid = m_op_type(nxt) == OP_GEMM;
+    if (ring_valid) m_issue_b_any<X3, RingDepth<TM>::value>(nxt, W, Wlo, lane, R);      // next task's first fragments fly during this epilogue (+ barrier)
+    m_gemm_epilogue<TM, X3, NT>(tk, S, lane, acc);
+#if HINT_MMA_EXP & 32
+    m_dbg_stamp(dbg, tid, 0);
+#endif
 }
 
 // ---- weight-gradient task ----------------------------------------------------------------------------------------------
@@ -470,6 +533,30 @@ HINT_DEV_CALL void m_dw(int r0, int r1, int r2, int r3, int r4, int r5, int r6, 
     }
 }
 
+// ---- op record / coupling table fetch (kernel parameter when the program fits it, else global memory) ---------------------
+HINT_DEV void m_ld_op(const MmaTables& T, const MmaParamProg& P, int idx, int (&r)[8]) {
+    if (T.in_param) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = P.ops[idx].w[i];
+        return;
+    }
+    const WOp* p = T.prog + idx;
+#if defined(__CUDA_ARCH__)
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(p)), q1 = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w; r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
+#else
+    for (int i = 0; i < 8; ++i) r[i] = p->w[i];
+#endif
+}
+HINT_DEV Ep m_ld_ep(const MmaTables& T, const MmaParamProg& P, int e) {
+    if (T.in_param) {
+        Ep ep;
+        ep.x_col = P.eps[e][0]; ep.s_col = P.eps[e][1]; ep.t_col = P.eps[e][2]; ep.pad = 0;
+        return ep;
+    }
+    return T.eps[e];
+}
+
 // ---- tile I/O and coupling epilogues (thread -> sample mapping as in simt_phases.cuh, for kMmaThreads threads) --------
 template <int TM>
 HINT_DEV void m_load_tile(int tid, float* S, int col_base, const float* __restrict__ gsrc, long long row0, long long B, int width) {
@@ -532,13 +619,13 @@ HINT_DEV void m_store_tile(int tid, const float* S, int col_base, float* __restr
 
 // hint.py:79-84.  forward: x_l <- e(s) x_l + t, J += alpha atan s;  inverse: x_l <- (x_l - t) / e(s), J -= alpha atan s
 template <int TM>
-HINT_DEV void m_coupling(int tid, float* S, const Ep* __restrict__ eps, int begin, int end, float alpha, int col_x,
+HINT_DEV void m_coupling(int tid, float* S, const MmaTables& T, const MmaParamProg& P, int begin, int end, float alpha, int col_x,
                          float* JP, bool rev) {
     constexpr int TMS = TM + 4, NJG = kMmaThreads / TM;
     const int m = tid % TM;
     float jacc = 0.f;
     for (int e = begin + tid / TM; e < end; e += NJG) {
-        const Ep ep = eps[(HINT_MMA_EXP & 4) ? begin : e];
+        const Ep ep = m_ld_ep(T, P, e);
         const float s = S[ep.s_col * TMS + m];
         const float t = S[ep.t_col * TMS + m];
         const float la = alpha * m_atan(s);
@@ -556,13 +643,13 @@ HINT_DEV void m_coupling(int tid, float* S, const Ep* __restrict__ eps, int begi
 
 // backward coupling: x_l' = (z_l - t)/e ; dt = dz_l ; ds = (dz_l (z_l - t) + dJ) alpha/(1+s^2) ; dx_l' = dz_l e
 template <int TM, bool ROUND>
-HINT_DEV void m_coupling_bwd(int tid, float* S, const Ep* __restrict__ eps, int begin, int end, float alpha, int col_x,
-                             int col_d, const float* DJ) {
+HINT_DEV void m_coupling_bwd(int tid, float* S, const MmaTables& T, const MmaParamProg& P, int begin, int end, float alpha,
+                             int col_x, int col_d, const float* DJ) {
     constexpr int TMS = TM + 4, NJG = kMmaThreads / TM;
     const int m = tid % TM;
     const float dj = DJ[m];
     for (int e = begin + tid / TM; e < end; e += NJG) {
-        const Ep ep = eps[e];
+        const Ep ep = m_ld_ep(T, P, e);
         float* sp = S + ep.s_col * TMS + m;
         float* tp = S + ep.t_col * TMS + m;
         float* xp = S + (col_x + ep.x_col) * TMS + m;
@@ -588,15 +675,6 @@ HINT_DEV int m_begin(const MmaTables& T, int warp) {
 }
 
 // ---- one tile through the tree: the warp interprets its op stream (plan_mma.h), next record always prefetched ------------
-HINT_DEV void m_ld_op(const WOp* __restrict__ p, int (&r)[8]) {
-#if defined(__CUDA_ARCH__)
-    const int4 q0 = __ldg(reinterpret_cast<const int4*>(p)), q1 = __ldg(reinterpret_cast<const int4*>(p) + 1);
-    r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w; r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
-#else
-    for (int i = 0; i < 8; ++i) r[i] = p->w[i];
-#endif
-}
-
 #define HINT_R8(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]
 template <int TM, bool X3>
 HINT_DEV void m_dw_dispatch(const int (&r)[8], const float* S, float* __restrict__ partial, bool first, int lane) {
@@ -617,41 +695,37 @@ HINT_DEV void m_dw_dispatch(const int (&r)[8], const float* S, float* __restrict
 // The interpreter.  BWD selects the backward coupling and enables the weight-gradient ops; `rev` the inverse coupling.
 // `cur` holds the warp's first record (loaded by the caller before the tile load).
 template <int TM, bool X3, bool BWD>
-HINT_DEV void m_run_program(const MmaTables& T, float* S, const float* __restrict__ W, const float* __restrict__ Wlo,
-                            float* __restrict__ partial, bool first, int tid, int rev, int (&cur)[8]) {
+HINT_DEV void m_run_program(const MmaTables& T, const MmaParamProg& P, float* S, const float* __restrict__ W,
+                            const float* __restrict__ Wlo, float* __restrict__ partial, bool first, int tid, int rev,
+                            int (&cur)[8], long long* dbg) {
     const int warp = tid >> 5, lane = tid & 31;
-    const WOp* pc = T.prog + m_begin(T, warp);
+    int pc = m_begin(T, warp);
     float* RAW = S + T.raw_off;
-    BRing<X3> R;
+    BRing<X3, RingDepth<TM>::value> R;
     bool ring_valid = false;   // R holds the first fragments of the next OP_GEMM
     for (;;) {
         const int type = m_op_type(cur);
         if (type == OP_END) break;
         int nxt[8];
-        m_ld_op(pc + 1, nxt);
-        if (lane == 0) m_prefetch_l1(pc + 8);     // keep the op stream a few records ahead in L1
+        m_ld_op(T, P, pc + 1, nxt);
+        if (!T.in_param && lane == 0) m_prefetch_l1(T.prog + pc + 8);     // keep the op stream a few records ahead in L1
         const bool sync = m_op_flags(cur) & MT_SYNC;
         if (type == OP_GEMM) {
-            const GemmOp tk = m_decode_gemm(cur);
             const int nt = m_gemm_nt(cur);
-            if (!ring_valid) m_issue_b<X3>(tk, nt, W, Wlo, lane, R);
-            if (sync) m_cta_sync();
-            float acc[TM / 16][kNC][4];
-            m_gemm_kloop<TM, X3>(tk, nt, S, W, Wlo, lane, R, acc);
-            ring_valid = m_op_type(nxt) == OP_GEMM;
-            if (ring_valid) m_issue_b<X3>(m_decode_gemm(nxt), m_gemm_nt(nxt), W, Wlo, lane, R);
-            m_gemm_epilogue<TM, X3>(tk, nt, S, lane, acc);
+            if (nt == 3) m_gemm_task<TM, X3, 3>(cur, nxt, sync, ring_valid, S, W, Wlo, lane, R, dbg, tid);
+            else if (nt == 2) m_gemm_task<TM, X3, 2>(cur, nxt, sync, ring_valid, S, W, Wlo, lane, R, dbg, tid);
+            else m_gemm_task<TM, X3, 1>(cur, nxt, sync, ring_valid, S, W, Wlo, lane, R, dbg, tid);
         } else {
             if (!ring_valid && m_op_type(nxt) == OP_GEMM) {
-                m_issue_b<X3>(m_decode_gemm(nxt), m_gemm_nt(nxt), W, Wlo, lane, R);
+                m_issue_b_any<X3, RingDepth<TM>::value>(nxt, W, Wlo, lane, R);
                 ring_valid = true;
             }
-            if (sync || type == OP_SYNC) m_cta_sync();
+            if (sync || type == OP_SYNC) { m_cta_sync(); m_dbg_stamp(dbg, tid, 0); }
             if (type == OP_DW) {
                 if (BWD) m_dw_dispatch<TM, X3>(cur, S, partial, first, lane);
             } else if (type == OP_COUPLE) {
-                if (BWD) m_coupling_bwd<TM, !X3>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, T.col_d, RAW);
-                else m_coupling<TM>(tid, S, T.eps, cur[0], cur[1], T.alpha, T.col_x, RAW, rev != 0);
+                if (BWD) m_coupling_bwd<TM, !X3>(tid, S, T, P, cur[0], cur[1], T.alpha, T.col_x, T.col_d, RAW);
+                else m_coupling<TM>(tid, S, T, P, cur[0], cur[1], T.alpha, T.col_x, RAW, rev != 0);
             }
         }
 #pragma unroll
@@ -661,17 +735,18 @@ HINT_DEV void m_run_program(const MmaTables& T, float* S, const float* __restric
 }
 
 template <int TM, bool X3>
-HINT_DEV void m_fwd_tile(const MmaTables& T, float* S, const float* __restrict__ x, const float* __restrict__ c,
+HINT_DEV void m_fwd_tile(const MmaTables& T, const MmaParamProg& P, float* S, const float* __restrict__ x, const float* __restrict__ c,
                          const float* __restrict__ W, const float* __restrict__ Wlo, float* __restrict__ z,
-                         float* __restrict__ logdet, long long B, int rev, long long row0, int tid) {
+                         float* __restrict__ logdet, long long B, int rev, long long row0, int tid, long long* dbg) {
     float* JP = S + T.raw_off;
+    m_dbg_stamp(dbg, tid, 0);
     int cur[8];
-    m_ld_op(T.prog + m_begin(T, tid >> 5), cur);
+    m_ld_op(T, P, m_begin(T, tid >> 5), cur);
     m_load_tile<TM>(tid, S, T.col_x, x, row0, B, T.d);
     m_load_tile<TM>(tid, S, T.col_x + T.d, c, row0, B, T.dc);
     JP[tid] = 0.f;
     m_cta_sync();
-    m_run_program<TM, X3, false>(T, S, W, Wlo, nullptr, false, tid, rev, cur);
+    m_run_program<TM, X3, false>(T, P, S, W, Wlo, nullptr, false, tid, rev, cur, dbg);
     m_store_tile<TM>(tid, S, T.col_x, z, row0, B, T.d);
     if (tid < TM && row0 + tid < B) {
         float j = 0.f;
@@ -682,21 +757,23 @@ HINT_DEV void m_fwd_tile(const MmaTables& T, float* S, const float* __restrict__
 }
 
 template <int TM, bool X3>
-HINT_DEV void m_bwd_tile(const MmaTables& T, float* S, const float* __restrict__ z, const float* __restrict__ c,
+HINT_DEV void m_bwd_tile(const MmaTables& T, const MmaParamProg& P, float* S, const float* __restrict__ z, const float* __restrict__ c,
                          const float* __restrict__ W, const float* __restrict__ Wlo, const float* __restrict__ dz,
                          const float* __restrict__ dlogdet, float* __restrict__ x_rec, float* __restrict__ dx,
-                         float* __restrict__ dc, float* __restrict__ partial, bool first, long long B, long long row0, int tid) {
+                         float* __restrict__ dc, float* __restrict__ partial, bool first, long long B, long long row0, int tid,
+                         long long* dbg) {
     constexpr int TMS = TM + 4;
     float* DJ = S + T.raw_off;
+    m_dbg_stamp(dbg, tid, 0);
     int cur[8];
-    m_ld_op(T.prog + m_begin(T, tid >> 5), cur);
+    m_ld_op(T, P, m_begin(T, tid >> 5), cur);
     m_load_tile<TM>(tid, S, T.col_x, z, row0, B, T.d);
     m_load_tile<TM>(tid, S, T.col_x + T.d, c, row0, B, T.dc);
     m_load_tile<TM>(tid, S, T.col_d, dz, row0, B, T.d);
     for (int i = tid; i < T.dc * TM; i += kMmaThreads) S[(T.col_d + T.d + i / TM) * TMS + i % TM] = 0.f;
     if (tid < TM) DJ[tid] = (row0 + tid < B) ? dlogdet[row0 + tid] : 0.f;
     m_cta_sync();
-    m_run_program<TM, X3, true>(T, S, W, Wlo, partial, first, tid, 0, cur);
+    m_run_program<TM, X3, true>(T, P, S, W, Wlo, partial, first, tid, 0, cur, dbg);
     if (x_rec) m_store_tile<TM>(tid, S, T.col_x, x_rec, row0, B, T.d);
     m_store_tile<TM>(tid, S, T.col_d, dx, row0, B, T.d);
     if (dc) m_store_tile<TM>(tid, S, T.col_d + T.d, dc, row0, B, T.dc);
@@ -714,27 +791,32 @@ HINT_DEV void m_init_consts(const MmaTables& T, float* S, int tid) {
 
 // whole-CTA bodies (persistent over tiles); `bid`/`nblocks` are blockIdx.x / gridDim.x
 template <int TM, bool X3>
-HINT_DEV void m_fwd_body(const MmaTables& T, float* S, const float* __restrict__ x, const float* __restrict__ c,
+HINT_DEV void m_fwd_body(const MmaTables& T, const MmaParamProg& P, float* S, const float* __restrict__ x, const float* __restrict__ c,
                          const float* __restrict__ W, const float* __restrict__ Wlo, float* __restrict__ z,
                          float* __restrict__ logdet, long long B, int rev, int tid, int bid, int nblocks) {
     m_init_consts<TM>(T, S, tid);
+    W += (bid % T.wcopies) * T.wstride;
+    if (X3) Wlo += (bid % T.wcopies) * T.wstride;
     const long long ntiles = (B + TM - 1) / TM;
     for (long long tile = bid; tile < ntiles; tile += nblocks)
-        m_fwd_tile<TM, X3>(T, S, x, c, W, Wlo, z, logdet, B, rev, tile * TM, tid);
+        m_fwd_tile<TM, X3>(T, P, S, x, c, W, Wlo, z, logdet, B, rev, tile * TM, tid, (bid == 0 && tile == nblocks) ? T.dbg : nullptr);
 }
 
 template <int TM, bool X3>
-HINT_DEV void m_bwd_body(const MmaTables& T, float* S, const float* __restrict__ z, const float* __restrict__ c,
+HINT_DEV void m_bwd_body(const MmaTables& T, const MmaParamProg& P, float* S, const float* __restrict__ z, const float* __restrict__ c,
                          const float* __restrict__ W, const float* __restrict__ Wlo, const float* __restrict__ dz,
                          const float* __restrict__ dlogdet, float* __restrict__ x_rec, float* __restrict__ dx,
                          float* __restrict__ dc, float* __restrict__ partials, long long n_partial, long long B, int tid,
                          int bid, int nblocks) {
     m_init_consts<TM>(T, S, tid);
+    W += (bid % T.wcopies) * T.wstride;
+    if (X3) Wlo += (bid % T.wcopies) * T.wstride;
     float* partial = partials + (long long)bid * n_partial;
     const long long ntiles = (B + TM - 1) / TM;
     bool first = true;
     for (long long tile = bid; tile < ntiles; tile += nblocks) {
-        m_bwd_tile<TM, X3>(T, S, z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partial, first, B, tile * TM, tid);
+        m_bwd_tile<TM, X3>(T, P, S, z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partial, first, B, tile * TM, tid,
+                           (bid == 0 && tile == nblocks) ? T.dbg : nullptr);
         first = false;
     }
 }
@@ -742,30 +824,32 @@ HINT_DEV void m_bwd_body(const MmaTables& T, float* S, const float* __restrict__
 #if defined(__CUDACC__)
 template <int TM, bool X3>
 __global__ void __launch_bounds__(kMmaThreads, HINT_MMA_MINB)
-hint_fwd_mma_kernel(MmaTables T, const float* __restrict__ x, const float* __restrict__ c, const float* __restrict__ W,
+hint_fwd_mma_kernel(const __grid_constant__ MmaTables T, const __grid_constant__ MmaParamProg P, const float* __restrict__ x, const float* __restrict__ c, const float* __restrict__ W,
                     const float* __restrict__ Wlo, float* __restrict__ z, float* __restrict__ logdet, long long B, int rev) {
     extern __shared__ float4 m_smem4[];
-    m_fwd_body<TM, X3>(T, reinterpret_cast<float*>(m_smem4), x, c, W, Wlo, z, logdet, B, rev, threadIdx.x, blockIdx.x, gridDim.x);
+    m_fwd_body<TM, X3>(T, P, reinterpret_cast<float*>(m_smem4), x, c, W, Wlo, z, logdet, B, rev, threadIdx.x, blockIdx.x, gridDim.x);
 }
 
 template <int TM, bool X3>
 __global__ void __launch_bounds__(kMmaThreads, HINT_MMA_MINB)
-hint_bwd_mma_kernel(MmaTables T, const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ W,
+hint_bwd_mma_kernel(const __grid_constant__ MmaTables T, const __grid_constant__ MmaParamProg P, const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ W,
                     const float* __restrict__ Wlo, const float* __restrict__ dz, const float* __restrict__ dlogdet,
                     float* __restrict__ x_rec, float* __restrict__ dx, float* __restrict__ dc, float* __restrict__ partials,
                     long long n_partial, long long B) {
     extern __shared__ float4 m_smem4[];
-    m_bwd_body<TM, X3>(T, reinterpret_cast<float*>(m_smem4), z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partials, n_partial, B,
+    m_bwd_body<TM, X3>(T, P, reinterpret_cast<float*>(m_smem4), z, c, W, Wlo, dz, dlogdet, x_rec, dx, dc, partials, n_partial, B,
                        threadIdx.x, blockIdx.x, gridDim.x);
 }
 
 __global__ void hint_pack_mma_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ hi,
-                                     float* __restrict__ lo, long long n) {
+                                     float* __restrict__ lo, long long n, int copies, long long stride) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float h, l;
         m_pack_elem(src[i], params, h, l);
-        hi[i] = h;
-        if (lo) lo[i] = l;
+        for (int c = 0; c < copies; ++c) {
+            hi[i + c * stride] = h;
+            if (lo) lo[i + c * stride] = l;
+        }
     }
 }
 #endif  // __CUDACC__

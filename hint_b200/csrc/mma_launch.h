@@ -15,9 +15,16 @@ struct DevMmaSchedule {
 
 struct DevMma {
     DevMmaSchedule fwd, bwd;
+    MmaParamProg* host_prog = nullptr;   // [3]: forward, inverse, backward programs in kernel-parameter form (host memory)
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
 };
+
+// The packed operands are written `mma_weight_copies()` times (stride mma_copy_stride floats): CTA b reads copy b % copies.
+// All CTAs walk the same op stream nearly in lock-step, so one copy makes 2*SMs CTAs hit the same few L2 lines at once.
+constexpr int kMmaWeightCopies = 1;   // measured on B200 (d=43 hint_8): 1, 4, 16, 64 copies within 5% - L2 is not the limiter
+int mma_weight_copies();
+long long mma_copy_stride(const MmaPlan& m);
 
 cudaError_t mma_setup(const MmaPlan& m, int num_sms, DevMma& d);
 void mma_free(DevMma& d);

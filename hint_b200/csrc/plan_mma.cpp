@@ -267,7 +267,7 @@ std::string build_mschedule(const Plan& p, MmaPlan& m, const std::vector<NodeOps
     int need_min = 0;
     for (const auto& n : p.nodes) need_min = std::max(need_min, 2 * round8(n.cout) + 4 * round8(n.h));
     struct Try { int tm; int budget; int ctas; };
-    const Try tries[] = {{64, (kSmemMax + 1024) / 2 - 1024, 2}, {64, kSmemMax, 1}, {32, kSmemMax, 1}, {16, kSmemMax, 1}};
+    const Try tries[] = {{64, (kSmemMax + 1024) / 2 - 1024, 2}, {64, kSmemMax, 1}, {32, kSmemMax, 1}};
     int TM = 0, avail = 0, raw_floats = 0;
     for (const Try& t : tries) {
         if (forced_tm > 0 && t.tm != forced_tm) continue;
@@ -393,7 +393,10 @@ std::string build_mschedule(const Plan& p, MmaPlan& m, const std::vector<NodeOps
             }
             for (; pending > 0; --pending) { MTask t{}; t.type = OP_SYNC; WOp so; std::memcpy(&so, &t, sizeof(so)); s.prog.push_back(so); }
             for (int e = 0; e < 3; ++e) { MTask t{}; t.type = OP_END; WOp so; std::memcpy(&so, &t, sizeof(so)); s.prog.push_back(so); }   // look-ahead padding
+            s.prog_end[pr] = (int)s.prog.size();
         }
+    for (int pr = 0; pr < nprog; ++pr)
+        s.fits_param[pr] = (s.prog_end[pr] - s.prog_begin[pr][0] <= kMaxProgOps) && ((int)s.eps.size() <= kMaxEps);
     s.ok = true;
     return "";
 }

@@ -69,6 +69,18 @@ static_assert(sizeof(DTask) == 32, "op records are 32 bytes");
 
 struct WOp { int w[8]; };
 static_assert(sizeof(WOp) == 32, "op records are 32 bytes");
+
+// The op streams (and the coupling table) of ONE launch travel as a __grid_constant__ kernel parameter when they fit the
+// 32 KB parameter space: the interpreter then fetches records through the constant cache instead of L1/L2 (with two
+// 113 KB CTAs per SM only ~20 KB of L1 are left, and a missed record costs an L2 round trip on the critical path of every
+// phase).  Larger programs stay in global memory (same interpreter, warp-uniform branch).
+constexpr int kMaxProgOps = 928;
+constexpr int kMaxEps = 256;
+struct MmaParamProg {
+    WOp ops[kMaxProgOps];
+    unsigned short eps[kMaxEps][4];   // x_col, s_col, t_col, pad
+};
+static_assert(sizeof(MmaParamProg) <= 32000, "must leave room for the other kernel arguments in the 32764-byte parameter space");
 enum { PROG_FWD = 0, PROG_INV = 1, PROG_BWD = 0 };
 
 enum {  // phases of a stage; forward kernels run PH_L1..PH_L3, backward all
@@ -97,6 +109,8 @@ struct MSchedule {
     std::vector<Ep> eps;
     std::vector<WOp> prog;      // all warps' op streams back to back
     int prog_begin[2][kMmaWarps] = {};   // [PROG_FWD | PROG_INV (forward schedule), PROG_BWD (backward schedule)][warp]
+    int prog_end[2] = {};       // one past the last record of each program
+    bool fits_param[2] = {};    // the program [prog_begin[p][0], prog_end[p]) and eps fit MmaParamProg
 };
 
 struct MmaPlan {

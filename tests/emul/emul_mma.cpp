@@ -140,29 +140,43 @@ namespace {
 MmaTables tables(const Plan& p, const MSchedule& s, int prog) {
     MmaTables t;
     t.prog = s.prog.data(); t.eps = s.eps.data();
-    for (int w = 0; w < kMmaWarps; ++w) t.begin[w] = s.prog_begin[prog][w];
+    t.in_param = s.fits_param[prog] ? 1 : 0;   // exercise the same record source the GPU launch would use
+    for (int w = 0; w < kMmaWarps; ++w) t.begin[w] = s.prog_begin[prog][w] - (t.in_param ? s.prog_begin[prog][0] : 0);
     t.d = p.d; t.dc = p.dc;
     t.col_x = s.col_x; t.col_d = s.col_d; t.col_one = s.col_one; t.col_zero = s.col_zero;
-    t.raw_off = s.raw_off; t.alpha = p.alpha;
+    t.raw_off = s.raw_off; t.alpha = p.alpha; t.dbg = nullptr; t.wcopies = 1; t.wstride = 0;
     return t;
 }
 
+void fill_param_prog(const MSchedule& s, int prog, MmaParamProg& P) {
+    std::memset(&P, 0, sizeof(P));
+    if (!s.fits_param[prog]) return;
+    const int b = s.prog_begin[prog][0], n = s.prog_end[prog] - b;
+    std::memcpy(P.ops, s.prog.data() + b, (size_t)n * sizeof(WOp));
+    for (size_t i = 0; i < s.eps.size(); ++i) {
+        P.eps[i][0] = (unsigned short)s.eps[i].x_col; P.eps[i][1] = (unsigned short)s.eps[i].s_col;
+        P.eps[i][2] = (unsigned short)s.eps[i].t_col; P.eps[i][3] = 0;
+    }
+}
+
 struct FwdArgs {
+    const MmaParamProg* P;
     MmaTables T; float* S; const float *x, *c, *W, *Wlo; float *z, *logdet; long long B; int rev, bid, nblocks, TM; bool x3;
 };
 template <int TM, bool X3>
 void fwd_body(int tid, void* a) {
     FwdArgs& A = *(FwdArgs*)a;
-    m_fwd_body<TM, X3>(A.T, A.S, A.x, A.c, A.W, A.Wlo, A.z, A.logdet, A.B, A.rev, tid, A.bid, A.nblocks);
+    m_fwd_body<TM, X3>(A.T, *A.P, A.S, A.x, A.c, A.W, A.Wlo, A.z, A.logdet, A.B, A.rev, tid, A.bid, A.nblocks);
 }
 struct BwdArgs {
+    const MmaParamProg* P;
     MmaTables T; float* S; const float *z, *c, *W, *Wlo, *dz, *dl; float *x_rec, *dx, *dc, *partials; long long n_partial, B;
     int bid, nblocks;
 };
 template <int TM, bool X3>
 void bwd_body(int tid, void* a) {
     BwdArgs& A = *(BwdArgs*)a;
-    m_bwd_body<TM, X3>(A.T, A.S, A.z, A.c, A.W, A.Wlo, A.dz, A.dl, A.x_rec, A.dx, A.dc, A.partials, A.n_partial, A.B, tid, A.bid, A.nblocks);
+    m_bwd_body<TM, X3>(A.T, *A.P, A.S, A.z, A.c, A.W, A.Wlo, A.dz, A.dl, A.x_rec, A.dx, A.dc, A.partials, A.n_partial, A.B, tid, A.bid, A.nblocks);
 }
 
 typedef void (*BodyFn)(int, void*);
@@ -170,7 +184,6 @@ BodyFn pick_fwd(int TM, bool x3) {
     switch (TM) {
         case 64: return x3 ? fwd_body<64, true> : fwd_body<64, false>;
         case 32: return x3 ? fwd_body<32, true> : fwd_body<32, false>;
-        case 16: return x3 ? fwd_body<16, true> : fwd_body<16, false>;
     }
     return nullptr;
 }
@@ -178,7 +191,6 @@ BodyFn pick_bwd(int TM, bool x3) {
     switch (TM) {
         case 64: return x3 ? bwd_body<64, true> : bwd_body<64, false>;
         case 32: return x3 ? bwd_body<32, true> : bwd_body<32, false>;
-        case 16: return x3 ? bwd_body<16, true> : bwd_body<16, false>;
     }
     return nullptr;
 }
@@ -202,7 +214,7 @@ int emul_mma_run(int d, int dc, const int* c_internal, int n_internal, double cl
     info[0] = m.fwd.TM; info[1] = m.bwd.TM; info[2] = (long long)m.fwd.smem_bytes; info[3] = (long long)m.bwd.smem_bytes;
     info[4] = (long long)m.fwd.stages.size(); info[5] = (long long)m.bwd.stages.size();
     info[6] = m.fwd.ctas_per_sm; info[7] = m.bwd.ctas_per_sm; info[8] = m.n_packed; info[9] = m.n_partial;
-    info[10] = (long long)m.fwd.mtasks.size(); info[11] = (long long)m.bwd.mtasks.size(); info[12] = (long long)m.bwd.dtasks.size();
+    info[13] = m.fwd.fits_param[0] + 2 * m.bwd.fits_param[0]; info[10] = (long long)m.fwd.mtasks.size(); info[11] = (long long)m.bwd.mtasks.size(); info[12] = (long long)m.bwd.dtasks.size();
     std::vector<float> W((size_t)m.n_packed + 4), Wlo((size_t)m.n_packed + 4);
     for (int64_t i = 0; i < m.n_packed; ++i) m_pack_elem(m.pack_src[(size_t)i], params, W[(size_t)i], Wlo[(size_t)i]);
     long long switches = 0;
@@ -210,11 +222,13 @@ int emul_mma_run(int d, int dc, const int* c_internal, int n_internal, double cl
         const MSchedule& s = m.fwd;
         BodyFn fn = pick_fwd(s.TM, x3 != 0);
         if (!fn) return 100;
+        static MmaParamProg PP;
+        fill_param_prog(s, rev ? PROG_INV : PROG_FWD, PP);
         const long long ntiles = (B + s.TM - 1) / s.TM;
         const int nb = (int)std::max<long long>(1, std::min<long long>(nctas, ntiles));
         for (int bid = 0; bid < nb; ++bid) {
             std::vector<float> S(s.smem_bytes / 4 + 16, NAN);
-            FwdArgs A{tables(p, s, rev ? PROG_INV : PROG_FWD), S.data(), x, c, W.data(), Wlo.data(), z, logdet, B, rev, bid, nb, s.TM, x3 != 0};
+            FwdArgs A{&PP, tables(p, s, rev ? PROG_INV : PROG_FWD), S.data(), x, c, W.data(), Wlo.data(), z, logdet, B, rev, bid, nb, s.TM, x3 != 0};
             emu::run_cta(kMmaThreads, fn, &A);
         }
     }
@@ -222,12 +236,14 @@ int emul_mma_run(int d, int dc, const int* c_internal, int n_internal, double cl
         const MSchedule& s = m.bwd;
         BodyFn fn = pick_bwd(s.TM, x3 != 0);
         if (!fn) return 101;
+        static MmaParamProg PP;
+        fill_param_prog(s, PROG_BWD, PP);
         const long long ntiles = (B + s.TM - 1) / s.TM;
         const int nb = (int)std::max<long long>(1, std::min<long long>(nctas, ntiles));
         std::vector<float> partials((size_t)nb * m.n_partial, NAN);
         for (int bid = 0; bid < nb; ++bid) {
             std::vector<float> S(s.smem_bytes / 4 + 16, NAN);
-            BwdArgs A{tables(p, s, PROG_BWD), S.data(), z, c, W.data(), Wlo.data(), dz, dl, x_rec, dx, dcond, partials.data(), m.n_partial, B, bid, nb};
+            BwdArgs A{&PP, tables(p, s, PROG_BWD), S.data(), z, c, W.data(), Wlo.data(), dz, dl, x_rec, dx, dcond, partials.data(), m.n_partial, B, bid, nb};
             emu::run_cta(kMmaThreads, fn, &A);
         }
         for (int64_t i = 0; i < p.n_params; ++i) {
@@ -236,7 +252,6 @@ int emul_mma_run(int d, int dc, const int* c_internal, int n_internal, double cl
             dparams[i] = a;
         }
     }
-    info[13] = switches;
     return 0;
 }
 }
