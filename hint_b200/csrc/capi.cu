@@ -14,6 +14,8 @@
 #include "plan_tc.h"
 #include "plan_mma.h"
 #include "mma_launch.h"
+#include "plan_chain.h"
+#include "chain_launch.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc2_kernels.cuh"
@@ -57,6 +59,7 @@ struct DevPlan {
     DevSchedule fwd, bwd;
     DevTc tc;
     DevMma mma;
+    DevChain chain;
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
     int num_sms = 0;
@@ -67,6 +70,7 @@ struct DevPlan {
 struct hint_plan {
     Plan p;
     MmaPlan mma;
+    ChainPlan chain;
     TcSchedule tc;
     T2Host tc2;
     std::mutex mu;
@@ -133,6 +137,9 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     CUDA_TRY(upload(&d.unpack_src, hp->p.unpack_src));
     if (hp->mma.ok) {
         CUDA_TRY(mma_setup(hp->mma, d.num_sms, d.mma));
+    }
+    if (hp->chain.ok) {
+        CUDA_TRY(chain_setup(hp->p, hp->chain, d.num_sms, d.chain));
     }
     if (hp->tc.ok) {
         CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
@@ -208,6 +215,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
         return fail(code, err);
     }
     build_mma_plan(hp->p, hp->mma);
+    build_chain_plan(hp->p, hp->chain);
     build_tc_schedule(hp->p, hp->tc);
     build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
@@ -226,6 +234,7 @@ void hint_plan_destroy(hint_plan_t* hp) {
         }
         cudaFree(d.pack_src); cudaFree(d.unpack_src);
         mma_free(d.mma);
+        chain_free(d.chain);
         cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
@@ -262,6 +271,7 @@ int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
         case HINT_MODE_FP32: return 1;
         case HINT_MODE_TF32: case HINT_MODE_TF32X3: case HINT_MODE_TF32_MMA: return hp->mma.ok ? 1 : 0;
         case HINT_MODE_TF32_TCGEN05: return hp->tc.ok ? 1 : 0;
+        case HINT_MODE_TF32_CHAIN: return (hp->chain.ok && hp->mma.ok) ? 1 : 0;
     }
     return 0;
 }
@@ -271,6 +281,7 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     if (!hp || B < 0) { fail(HINT_ERR_INVALID, "bad plan or batch"); return 0; }
     size_t bytes = align256((size_t)std::max<long long>(hp->p.n_packed, hp->tc.ok ? hp->tc.n_packed : 0) * 4);
     if (hp->mma.ok) bytes = std::max(bytes, mma_packed_bytes(hp->mma));
+    if (hp->chain.ok) bytes = std::max(bytes, align256((size_t)hp->chain.n_packed * 4));
     if (which == HINT_WS_BACKWARD) {
         DevPlan* d = nullptr;
         if (get_dev(hp, &d) != HINT_OK) return 0;
@@ -285,8 +296,11 @@ static int check_common(const hint_plan* hp, const float* x, const float* c, con
     if (!hp) return fail(HINT_ERR_INVALID, "plan is NULL");
     if (B < 0) return fail(HINT_ERR_INVALID, "negative batch");
     if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32 && mode != HINT_MODE_TF32X3 && mode != HINT_MODE_TF32_TCGEN05 &&
-        mode != HINT_MODE_TF32_MMA)
+        mode != HINT_MODE_TF32_MMA && mode != HINT_MODE_TF32_CHAIN)
         return fail(HINT_ERR_INVALID, "unknown mode");
+    if (mode == HINT_MODE_TF32_CHAIN && !hp->chain.ok)
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the register-chained kernels' envelope: " + hp->chain.why);
+    if (mode == HINT_MODE_TF32_CHAIN) mode = HINT_MODE_TF32_MMA;   // same requirements otherwise
     if ((mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3 || mode == HINT_MODE_TF32_MMA) && !hp->mma.ok)
         return fail(HINT_ERR_UNSUPPORTED, "this block is outside the warp-MMA kernels' envelope: " + hp->mma.why);
     if (mode == HINT_MODE_TF32_TCGEN05 && !hp->tc.ok)
@@ -318,8 +332,15 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     // explicitly (tests run both).
     if (mode == HINT_MODE_TF32) {
         static const char* pref = std::getenv("HINT_B200_TF32_FWD");
+        const bool want_chain = pref ? std::strcmp(pref, "chain") == 0 : true;
         const bool want_tc = pref ? std::strcmp(pref, "tcgen05") == 0 : true;
-        mode = (want_tc && hp->tc.ok && hp->tc2.ok) ? HINT_MODE_TF32_TCGEN05 : HINT_MODE_TF32_MMA;
+        mode = (want_chain && hp->chain.ok) ? HINT_MODE_TF32_CHAIN
+               : (want_tc && hp->tc.ok && hp->tc2.ok) ? HINT_MODE_TF32_TCGEN05 : HINT_MODE_TF32_MMA;
+    }
+    if (mode == HINT_MODE_TF32_CHAIN) {
+        CUDA_TRY(chain_pack(hp->chain, d->chain, params, packed, st));
+        CUDA_TRY(chain_launch_fwd(hp->p, hp->chain, d->chain, x, c, packed, z, logdet, (long long)B, rev ? 1 : 0, st));
+        return HINT_OK;
     }
     if (mode == HINT_MODE_TF32_MMA || mode == HINT_MODE_TF32X3) {
         const bool x3 = mode == HINT_MODE_TF32X3;

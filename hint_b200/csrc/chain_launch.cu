@@ -1,0 +1,105 @@
+// Launch glue of the register-chained warp-MMA kernels.
+#include "chain_launch.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "chain_kernels.cuh"
+
+namespace hint {
+
+namespace {
+
+// forward / inverse configuration: MT = 1 (16 samples per warp) with as many warps as fit next to the shared-memory
+// resident operands (WS), else 16 warps reading the operands through L1.  HINT_B200_CHAIN_FWD=<mt><nw><ws> (e.g. "2080",
+// "1161") overrides (developer aid).
+struct FwdCfg { int mt, nw, ws; size_t smem; };
+
+template <int MT, int NW, bool WS>
+cudaError_t set_attr() {
+    cudaError_t e = cudaFuncSetAttribute((const void*)hint_fwd_chain_kernel<MT, NW, false, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute((const void*)hint_fwd_chain_kernel<MT, NW, true, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+}
+
+size_t fwd_smem(const Plan& p, const ChainPlan& c, int mt, int nw, int ws) {
+    return mt == 2 ? chain_fwd_smem_bytes<2>(c.n_nodes, p.d, p.dc, nw, c.n_fwd_packed, ws != 0)
+                   : chain_fwd_smem_bytes<1>(c.n_nodes, p.d, p.dc, nw, c.n_fwd_packed, ws != 0);
+}
+
+FwdCfg pick_fwd(const Plan& p, const ChainPlan& c) {
+    static const char* e = std::getenv("HINT_B200_CHAIN_FWD");
+    if (e && e[0] && e[1] && e[2] && e[3]) {
+        FwdCfg f{e[0] - '0', 10 * (e[1] - '0') + (e[2] - '0'), e[3] - '0', 0};
+        f.smem = fwd_smem(p, c, f.mt, f.nw, f.ws);
+        return f;
+    }
+    for (int nw : {16, 12, 8}) {
+        const size_t b = fwd_smem(p, c, 1, nw, 1);
+        if (b <= (size_t)kSmemMax) return FwdCfg{1, nw, 1, b};
+    }
+    return FwdCfg{1, 16, 0, fwd_smem(p, c, 1, 16, 0)};
+}
+
+template <typename T>
+cudaError_t upload(T** dst, const std::vector<T>& v) {
+    *dst = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+cudaError_t chain_setup(const Plan& p, const ChainPlan& c, int num_sms, DevChain& d) {
+    cudaError_t e;
+    d.num_sms = num_sms;
+    const FwdCfg f = pick_fwd(p, c);
+    d.fwd_smem = f.smem;
+    if (d.fwd_smem > (size_t)kSmemMax) return cudaErrorInvalidValue;
+    if ((e = set_attr<1, 16, true>()) != cudaSuccess) return e;
+    if ((e = set_attr<1, 12, true>()) != cudaSuccess) return e;
+    if ((e = set_attr<1, 8, true>()) != cudaSuccess) return e;
+    if ((e = set_attr<1, 16, false>()) != cudaSuccess) return e;
+    if ((e = set_attr<2, 8, true>()) != cudaSuccess) return e;
+    if ((e = set_attr<2, 8, false>()) != cudaSuccess) return e;
+    if ((e = upload(&d.pack_src, c.pack_src)) != cudaSuccess) return e;
+    return upload(&d.unpack_src, c.unpack_src);
+}
+
+void chain_free(DevChain& d) {
+    cudaFree(d.pack_src); cudaFree(d.unpack_src);
+    d.pack_src = d.unpack_src = nullptr;
+}
+
+cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* params, float* packed, cudaStream_t st) {
+    const long long n = c.n_packed;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
+    hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, nullptr, n, 1, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t chain_launch_fwd(const Plan& p, const ChainPlan& c, const DevChain& d, const float* x, const float* cond,
+                             const float* packed, float* z, float* logdet, long long B, int rev, cudaStream_t st) {
+    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed};
+    const FwdCfg f = pick_fwd(p, c);
+    const int RW = 16 * f.mt;
+    const long long ntiles = (B + RW - 1) / RW;
+    const int grid = (int)std::min<long long>((ntiles + f.nw - 1) / f.nw, d.num_sms);
+#define HINT_CHAIN_LAUNCH(MT, NW, WS)                                                                                          \
+    if (f.mt == MT && f.nw == NW && f.ws == WS) {                                                                              \
+        if (rev) hint_fwd_chain_kernel<MT, NW, true, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B);  \
+        else hint_fwd_chain_kernel<MT, NW, false, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B);     \
+        return cudaGetLastError();                                                                                             \
+    }
+    HINT_CHAIN_LAUNCH(1, 16, 1) HINT_CHAIN_LAUNCH(1, 12, 1) HINT_CHAIN_LAUNCH(1, 8, 1) HINT_CHAIN_LAUNCH(1, 16, 0)
+    HINT_CHAIN_LAUNCH(2, 8, 1) HINT_CHAIN_LAUNCH(2, 8, 0)
+#undef HINT_CHAIN_LAUNCH
+    return cudaErrorInvalidValue;
+
+}
+
+}  // namespace hint

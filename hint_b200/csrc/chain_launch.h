@@ -1,0 +1,24 @@
+// Host-side launch interface of the register-chained warp-MMA kernels (chain_kernels.cuh), compiled in its own
+// translation unit (chain_launch.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plan_chain.h"
+
+namespace hint {
+
+struct DevChain {
+    int* pack_src = nullptr;
+    int* unpack_src = nullptr;
+    int num_sms = 0;
+    size_t fwd_smem = 0, bwd_smem = 0;
+    int bwd_ctas = 0;
+};
+
+cudaError_t chain_setup(const Plan& p, const ChainPlan& c, int num_sms, DevChain& d);
+void chain_free(DevChain& d);
+cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* params, float* packed, cudaStream_t st);
+cudaError_t chain_launch_fwd(const Plan& p, const ChainPlan& c, const DevChain& d, const float* x, const float* cond,
+                             const float* packed, float* z, float* logdet, long long B, int rev, cudaStream_t st);
+
+}  // namespace hint

@@ -841,7 +841,7 @@ hint_bwd_mma_kernel(const __grid_constant__ MmaTables T, const __grid_constant__
                        threadIdx.x, blockIdx.x, gridDim.x);
 }
 
-__global__ void hint_pack_mma_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ hi,
+static __global__ void hint_pack_mma_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ hi,
                                      float* __restrict__ lo, long long n, int copies, long long stride) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float h, l;

@@ -43,6 +43,9 @@ extern "C" {
 #define HINT_MODE_TF32_MMA 4    /* HINT_MODE_TF32 with the warp-MMA kernel forced for forward/inverse too (HINT_MODE_TF32
                                    itself picks the faster of the two forward kernels the block fits)                */
 
+#define HINT_MODE_TF32_CHAIN 5  /* HINT_MODE_TF32 with the register-chained warp-MMA kernels forced (HINT_MODE_TF32 picks
+                                   them whenever the block fits their shape table)                                   */
+
 /* which workspace hint_workspace_bytes() sizes */
 #define HINT_WS_FORWARD 0
 #define HINT_WS_BACKWARD 1

@@ -1,0 +1,55 @@
+// Host emulation of the register-chained warp-MMA kernels (chain_kernels.cuh).  TEST INFRASTRUCTURE ONLY: built and loaded
+// by tests/test_emul_chain.py on CPU-only machines; never linked into libhint_b200.so, never used by the product.
+// Reuses the fiber scheduler and the mma.sync model of emul_mma.cpp.
+#include "emul_mma.cpp"
+
+#include "../../hint_b200/csrc/plan_chain.h"
+#include "../../hint_b200/csrc/chain_kernels.cuh"
+
+namespace {
+
+struct CFwdArgs {
+    ChainTables T; const ChainNode* P; float* S; const float *x, *c, *W; float *z, *logdet; long long B; int bid, nblocks;
+};
+template <int MT, bool REV>
+void cfwd_body(int tid, void* a) {
+    CFwdArgs& A = *(CFwdArgs*)a;
+    c_fwd_body<MT, (MT == 2 ? 8 : 16), REV, false>(A.T, A.P, A.S, A.x, A.c, A.W, A.z, A.logdet, A.B, tid, A.bid, A.nblocks);
+}
+
+}  // namespace
+
+extern "C" {
+// info: {ok, n_packed, n_partial, n_nodes, max_nh}
+int emul_chain_run(int d, int dc, const int* c_internal, int n_internal, double clamp, int max_splits, int min_split_size,
+                   const float* params, const float* x, const float* c, long long B, int rev, int nctas, int mt,
+                   float* z, float* logdet, const float* dz, const float* dl, float* x_rec, float* dx, float* dcond,
+                   float* dparams, long long* info) {
+    Plan p;
+    int code = 0;
+    std::string err = build_plan(p, d, dc, c_internal, n_internal, clamp, max_splits, min_split_size, 0, &code);
+    if (!err.empty()) return code ? code : 1;
+    ChainPlan cp;
+    build_chain_plan(p, cp);
+    info[0] = cp.ok; info[1] = cp.n_packed; info[2] = cp.n_partial; info[3] = cp.n_nodes; info[4] = cp.max_nh;
+    if (!cp.ok) return 50;
+    std::vector<float> W((size_t)cp.n_packed + 4);
+    for (int64_t i = 0; i < cp.n_packed; ++i) { float lo; m_pack_elem(cp.pack_src[(size_t)i], params, W[(size_t)i], lo); }
+    ChainTables T{cp.n_nodes, p.d, p.dc, p.alpha, (int)cp.n_fwd_packed};
+    {
+        const int RW = 16 * mt;
+        const long long ntiles = (B + RW - 1) / RW;
+        const int nw = mt == 2 ? 8 : 16;
+        const int nb = (int)std::max<long long>(1, std::min<long long>(nctas, (ntiles + nw - 1) / nw));
+        const size_t wf = mt == 2 ? chain_fwd_warp_floats<2>(p.d, p.dc) : chain_fwd_warp_floats<1>(p.d, p.dc);
+        for (int bid = 0; bid < nb; ++bid) {
+            std::vector<float> S(wf * nw + 16, NAN);
+            CFwdArgs A{T, cp.param.nodes, S.data(), x, c, W.data(), z, logdet, B, bid, nb};
+            void (*fn)(int, void*) = mt == 2 ? (rev ? cfwd_body<2, true> : cfwd_body<2, false>) : (rev ? cfwd_body<1, true> : cfwd_body<1, false>);
+            emu::run_cta(32 * nw, fn, &A);
+        }
+    }
+    (void)dz; (void)dl; (void)x_rec; (void)dx; (void)dcond; (void)dparams;
+    return 0;
+}
+}

@@ -37,7 +37,7 @@ struct Cta {
     ucontext_t main;
     int bar_count = 0;
     unsigned bar_gen = 0;
-    WarpX warps[kMmaWarps];
+    WarpX warps[32];
     void (*body)(int tid, void* arg) = nullptr;
     void* arg = nullptr;
     long long switches = 0;
@@ -63,6 +63,8 @@ static void warp_rendezvous(WarpX& w) {
     if (++w.count == 32) { w.count = 0; ++w.gen; }
     else while (w.gen == gen) yield_fiber();
 }
+
+void warp_sync() { warp_rendezvous(g_cta->warps[g_cta->cur >> 5]); }
 
 static inline float tf32(uint32_t u) {
     u &= 0xFFFFE000u;
@@ -102,7 +104,7 @@ static void trampoline() {
     swapcontext(&c->ctx[tid], &c->main);
 }
 
-static void run_cta(int nthreads, void (*body)(int, void*), void* arg) {
+void run_cta(int nthreads, void (*body)(int, void*), void* arg) {
     Cta cta;
     cta.n = nthreads;
     cta.ctx.resize(nthreads);
