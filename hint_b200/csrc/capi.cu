@@ -287,6 +287,7 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
         if (get_dev(hp, &d) != HINT_OK) return 0;
         size_t part = align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
         if (hp->mma.ok) part = std::max(part, align256((size_t)mma_bwd_ctas(hp->mma, *d, B) * (size_t)hp->mma.n_partial * 4));
+        if (hp->chain.ok) part = std::max(part, align256((size_t)chain_bwd_ctas(hp->chain, d->chain, B) * (size_t)hp->chain.n_partial * 4));
         bytes += part;
     }
     return bytes + 256;
@@ -445,6 +446,13 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
     int rc = check_common(hp, z, c, params, B, mode == HINT_MODE_TF32_TCGEN05 ? HINT_MODE_FP32 : mode);
     if (rc != HINT_OK) return rc;
     if (!dparams) return fail(HINT_ERR_INVALID, "dparams is NULL");
+    // HINT_MODE_TF32 backward: the register-chained kernel where the block fits its shape table, else the interpreter
+    // warp-MMA kernel.  HINT_B200_TF32_BWD=mma forces the latter (developer aid; HINT_MODE_TF32_MMA does the same).
+    bool use_chain = mode == HINT_MODE_TF32_CHAIN;
+    if (mode == HINT_MODE_TF32 && hp->chain.ok) {
+        static const char* pref = std::getenv("HINT_B200_TF32_BWD");
+        use_chain = !(pref && std::strcmp(pref, "mma") == 0);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) {
         CUDA_TRY(cudaMemsetAsync(dparams, 0, (size_t)hp->p.n_params * 4, st));
@@ -458,7 +466,19 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
     if (!workspace || workspace_bytes < hint_workspace_bytes(hp, B, HINT_WS_BACKWARD))
         return fail(HINT_ERR_WORKSPACE, "workspace too small");
     float* packed = reinterpret_cast<float*>(workspace);
-    if (mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3 || mode == HINT_MODE_TF32_MMA) {
+    if (use_chain) {
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->chain.n_packed * 4));
+        CUDA_TRY(chain_pack(hp->chain, d->chain, params, packed, st));
+        const int grid = chain_bwd_ctas(hp->chain, d->chain, (long long)B);
+        CUDA_TRY(chain_launch_bwd(hp->p, hp->chain, d->chain, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, (long long)B, st));
+        const long long n = hp->p.n_params;
+        const int threads = 256;
+        const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->chain.unpack_src, partials, grid, (long long)hp->chain.n_partial, dparams, n);
+        CUDA_TRY(cudaGetLastError());
+        return HINT_OK;
+    }
+    if (mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3 || mode == HINT_MODE_TF32_MMA || mode == HINT_MODE_TF32_CHAIN) {
         const bool x3 = mode == HINT_MODE_TF32X3;
         float* hi = packed;
         float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mma_half_bytes(hp->mma));

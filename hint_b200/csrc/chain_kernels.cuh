@@ -333,4 +333,454 @@ hint_fwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
 }
 #endif
 
+
+// =====================================================================================================================
+// Backward (memory-free; the autograd tape of hint.py:62-101): input is the block OUTPUT z.  Nodes are walked
+// parent-first (the inverse order, hint.py:85-88).  A CTA owns a tile of TM = 16*MT*NW samples; the tile state lives in
+// CTA-wide shared-memory columns [column][sample] with an XOR swizzle of the 16-byte chunks (c_swz) so that BOTH access
+// patterns are bank-conflict free: a warp's private rows of the column pairs (2t, 2t+1) - the C/A fragment pattern of the
+// register-chained subnets - and 4 consecutive samples of 8 consecutive columns - the operand pattern of the weight-gradient
+// GEMMs, which contract over the tile's samples.  Per node and net:
+//   private (each warp its own 16*MT samples, everything in registers): recompute the subnet, coupling backward
+//     x_l' = (z_l - t)/e, dx_l' = dz_l e, ds = (dz_l (z_l - t) + dJ) alpha/(1+s^2), dt = dz_l, then the dgrad chain
+//     dh2 = (dout W3) [h2>0], dh1 = (dh2 W2) [h1>0], dx_u' += dh1 W1; h1, h2, dh1, dh2, dout are also written (tf32) to the
+//     CTA-wide buffers HB1, HB2, GB1, GB2, GO;
+//   barrier; cooperative: dW3T += [h2|1]^T dout, dW2T += [h1|1]^T dh2, dW1T += [a|1]^T dh1 as m16n8k8 MMAs with K = the
+//     TM samples of the tile, output tiles dealt round-robin to the warps, flushed to the CTA's private partial-gradient
+//     buffer (store on the first tile, red.global.add afterwards; reduced in fixed order by hint_reduce_unpack_kernel);
+//   barrier.
+HINT_DEV int c_swz(int col) { return (((col >> 1) & 3) << 1) ^ ((col & 1) << 2); }
+
+// float index of the lane's R = 2*MT rows (samples 16*MT*warp + R*g ..) of column `col`
+template <int MT, int NW>
+HINT_DEV int c_rows(int col, int warp, int g) {
+    constexpr int TM = 16 * MT * NW;
+    if (MT == 2) return col * TM + (((8 * warp + g) ^ c_swz(col)) << 2);
+    return col * TM + (((4 * warp + (g >> 1)) ^ c_swz(col)) << 2) + 2 * (g & 1);
+}
+// float index of sample m of column col
+template <int TM>
+HINT_DEV int c_elem(int col, int m) { return col * TM + ((((m >> 2) ^ c_swz(col))) << 2) + (m & 3); }
+
+struct ChainBwdSmem {      // float offsets of the CTA's shared-memory regions
+    int xt, dz, hb1, hb2, gb1, gb2, go, dj, nodes, total;
+};
+template <int MT, int NW>
+HINT_HD constexpr ChainBwdSmem chain_bwd_smem(int d, int dc, int max_nh, int max_no, int n_nodes) {
+    constexpr int TM = 16 * MT * NW;
+    ChainBwdSmem s{};
+    const int xc = (d + dc + 7) & ~7;     // buffers start at multiples of 8 columns (swizzle phase of the fragment columns)
+    s.xt = 0;
+    s.dz = s.xt + xc * TM;
+    s.hb1 = s.dz + xc * TM;
+    s.hb2 = s.hb1 + 8 * max_nh * TM;
+    s.gb1 = s.hb2 + 8 * max_nh * TM;
+    s.gb2 = s.gb1 + 8 * max_nh * TM;
+    s.go = s.gb2 + 8 * max_nh * TM;
+    s.dj = s.go + 8 * max_no * TM;
+    s.nodes = s.dj + TM;
+    s.total = s.nodes + 8 * n_nodes;
+    return s;
+}
+
+template <int MT, int NW, int KS1>
+HINT_DEV void c_load_input_sw(const float* XT, int lo, int k, int cin, int d, int warp, int lane, uint32_t (&a)[KS1][MT][4]) {
+    constexpr int R = 2 * MT;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < KS1; ++ks)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int f = 8 * ks + 2 * t + c;
+            float v[R];
+#pragma unroll
+            for (int e = 0; e < R; ++e) v[e] = 0.f;
+            if (f < cin) c_ld_rows<MT>(XT + c_rows<MT, NW>(f < k ? lo + f : d + (f - k), warp, g), v);
+#pragma unroll
+            for (int i = 0; i < MT; ++i) { a[ks][i][2 * c] = m_rna(v[2 * i]); a[ks][i][2 * c + 1] = m_rna(v[2 * i + 1]); }
+        }
+}
+
+// A fragments (already ReLU'd and rounded) -> the warp's rows of a hidden buffer.  rp[c] = the lane's row address of buffer
+// column 2t+c; n-tile j is 8*j*TM floats further.
+template <int MT, int TM, int NT>
+HINT_DEV void c_store_afrag(float* buf, const int (&rp)[2], const uint32_t (&a)[NT][MT][4]) {
+    constexpr int R = 2 * MT;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float v[R];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) { v[2 * i] = m_float(a[j][i][2 * c]); v[2 * i + 1] = m_float(a[j][i][2 * c + 1]); }
+            c_st_rows<MT>(buf + rp[c] + 8 * j * TM, v);
+        }
+}
+
+// dgrad epilogue: G (C fragments) masked by the stored forward activation (> 0 <=> its rounded bits exceed the rounding
+// increment), rounded to tf32 -> A fragments of the next dgrad layer
+template <int MT, int TM, int NT>
+HINT_DEV void c_mask_to_a(const float (&acc)[NT][MT][4], const float* hbuf, const int (&rp)[2], uint32_t (&a)[NT][MT][4]) {
+    constexpr int R = 2 * MT;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float hv[R];
+            c_ld_rows<MT>(hbuf + rp[c] + 8 * j * TM, hv);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    a[j][i][2 * c + hh] = m_bits(hv[2 * i + hh]) > 0x1000u ? m_rna(acc[j][i][2 * hh + c]) : 0u;
+        }
+}
+
+// weight-gradient GEMM of one layer: CT[in-feature rows | ones row][out cols] += sum over the tile's samples.
+//   XIN: the in-features are the node's subnet inputs (x_upper' / condition columns of the x tile), else columns of `abuf`.
+template <int MT, int NW, int KSIN, int NTOUT, bool XIN>
+HINT_DEV void c_dw_gemm(const float* abuf, int lo, int k, int cin, int d, const float* bbuf, float* __restrict__ part, bool first,
+                        int warp, int lane) {
+    constexpr int TM = 16 * MT * NW;
+    constexpr int MTC = chain_dw_mt(KSIN);
+    constexpr int NC = NTOUT <= 5 ? NTOUT : 3;
+    constexpr int NCH = NTOUT / NC;
+    static_assert(NCH * NC == NTOUT, "n-chunking must tile the layer");
+    const int g = lane >> 2, t = lane & 3;
+    for (int u = warp; u < MTC * NCH; u += NW) {
+        const int i = u / NCH, ch = u - i * NCH;
+        // A rows r0 = 16i + g, r1 = r0 + 8: feature column, the ones row (bias) or zero padding
+        int abase[2], amode[2];      // amode 0 load, 1 ones, 2 zero
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r = 16 * i + 8 * hh + g;
+            int col = 0;
+            amode[hh] = 0;
+            if (XIN) {
+                if (r < cin) col = r < k ? lo + r : d + (r - k);
+                else amode[hh] = (r == 8 * KSIN) ? 1 : 2;
+            } else {
+                if (r < 8 * KSIN) col = r;
+                else amode[hh] = (r == 8 * KSIN) ? 1 : 2;
+            }
+            const int sw = c_swz(col);
+            abase[hh] = col * TM + (((t ^ sw) & 3) << 2) + ((sw >> 2) << 4);
+        }
+        int bbase[NC];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) {
+            const int col = 8 * (ch * NC + jj) + g;
+            const int sw = c_swz(col);
+            bbase[jj] = col * TM + (((t ^ sw) & 3) << 2) + ((sw >> 2) << 4);
+        }
+        float acc[NC][4];
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[jj][e] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < TM / 16; ++kk) {
+            float av[2][4];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (amode[hh] == 0) {
+                    const float* p = abuf + (abase[hh] ^ (kk << 4));
+#if defined(__CUDA_ARCH__)
+                    const float4 q = *reinterpret_cast<const float4*>(p);
+                    av[hh][0] = q.x; av[hh][1] = q.y; av[hh][2] = q.z; av[hh][3] = q.w;
+#else
+                    for (int e = 0; e < 4; ++e) av[hh][e] = p[e];
+#endif
+                } else {
+                    const float v = amode[hh] == 1 ? 1.f : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) av[hh][e] = v;
+                }
+            }
+            uint32_t a0[4] = {m_bits(av[0][0]), m_bits(av[1][0]), m_bits(av[0][1]), m_bits(av[1][1])};
+            uint32_t a1[4] = {m_bits(av[0][2]), m_bits(av[1][2]), m_bits(av[0][3]), m_bits(av[1][3])};
+            if (XIN) {   // x columns are exact fp32: round them like every other operand
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a0[e] += 0x1000u; a1[e] += 0x1000u; }
+            }
+#pragma unroll
+            for (int jj = 0; jj < NC; ++jj) {
+                const float* p = bbuf + (bbase[jj] ^ (kk << 4));
+                float bv[4];
+#if defined(__CUDA_ARCH__)
+                const float4 q = *reinterpret_cast<const float4*>(p);
+                bv[0] = q.x; bv[1] = q.y; bv[2] = q.z; bv[3] = q.w;
+#else
+                for (int e = 0; e < 4; ++e) bv[e] = p[e];
+#endif
+                m_mma(acc[jj], a0, m_bits(bv[0]), m_bits(bv[1]));
+                m_mma(acc[jj], a1, m_bits(bv[2]), m_bits(bv[3]));
+            }
+        }
+        // flush: C fragment (i, j) = 128 floats, the lane's 4 are contiguous
+        {
+#pragma unroll
+            for (int jj = 0; jj < NC; ++jj) {
+                float* q = part + ((i * NTOUT + ch * NC + jj) * 32 + lane) * 4;
+#if defined(__CUDA_ARCH__)
+                if (first) *reinterpret_cast<float4*>(q) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+                else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]) : "memory");
+#else
+                for (int e = 0; e < 4; ++e) { if (first) q[e] = acc[jj][e]; else q[e] += acc[jj][e]; }
+#endif
+            }
+        }
+    }
+}
+
+// one tree node of the backward sweep
+template <int MT, int NW, int KS1, int NH, int NO>
+HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, const float* __restrict__ Wn, const float* __restrict__ Wt,
+                         float* S, const ChainBwdSmem& L, float* __restrict__ part, bool first, int warp, int lane) {
+    constexpr int TM = 16 * MT * NW, R = 2 * MT;
+    const int g = lane >> 2, t = lane & 3;
+    float* XT = S + L.xt;
+    float* DZ = S + L.dz;
+    // the lane's row addresses of buffer columns 2t, 2t+1 (same in every buffer that starts at a multiple of 8 columns)
+    int rp[2];
+    rp[0] = c_rows<MT, NW>(2 * t, warp, g);
+    rp[1] = c_rows<MT, NW>(2 * t + 1, warp, g);
+    uint32_t a1[KS1][MT][4];
+    c_load_input_sw<MT, NW, KS1>(XT, lo, k, cin, d, warp, lane, a1);
+    uint32_t dout[2][NO][MT][4];      // ds, dt as A fragments
+    {
+        float s[NO][MT][4], tt[NO][MT][4];
+        c_subnet<false, MT, KS1, NH, NO>(a1, Wn + chain_net_floats(KS1, NH, NO), lane, tt);
+        {   // s subnet, keeping h1 / h2 in the CTA-wide buffers
+            uint32_t h[NH][MT][4];
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, KS1, NH>(a1, Wn + chain_w1(KS1, NH, NO), Wn + chain_b1(KS1, NH, NO), lane, acc);
+                c_relu_to_a<MT, NH>(acc, h);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, NH, NH>(h, Wn + chain_w2(KS1, NH, NO), Wn + chain_b2(KS1, NH, NO), lane, acc);
+                c_relu_to_a<MT, NH>(acc, h);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
+            c_layer<false, MT, NH, NO>(h, Wn + chain_w3(KS1, NH, NO), Wn + chain_b3(KS1, NH, NO), lane, s);
+        }
+        // coupling backward on the C fragments
+        float dj[R];
+        c_ld_rows<MT>(S + L.dj + 16 * MT * warp + R * g, dj);
+#pragma unroll
+        for (int j = 0; j < NO; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = 8 * j + 2 * t + c;
+                float dsv[R], dtv[R];
+#pragma unroll
+                for (int e = 0; e < R; ++e) { dsv[e] = 0.f; dtv[e] = 0.f; }
+                if (col < cout) {
+                    const int ra = c_rows<MT, NW>(lo + k + col, warp, g);
+                    float zl[R], dzl[R];
+                    c_ld_rows<MT>(XT + ra, zl);
+                    c_ld_rows<MT>(DZ + ra, dzl);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int e = 2 * i + hh;
+                            const float sv = s[j][i][2 * hh + c], tv = tt[j][i][2 * hh + c];
+                            const float la = alpha * m_atan(sv);
+                            const float r = zl[e] - tv;
+                            zl[e] = r * m_exp(-la);
+                            dsv[e] = (dzl[e] * r + dj[e]) * (alpha * m_rcp(fmaf(sv, sv, 1.f)));
+                            dtv[e] = dzl[e];
+                            dzl[e] = dzl[e] * m_exp(la);
+                        }
+                    c_st_rows<MT>(XT + ra, zl);
+                    c_st_rows<MT>(DZ + ra, dzl);
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        dout[0][j][i][2 * c + hh] = m_rna(dsv[2 * i + hh]);
+                        dout[1][j][i][2 * c + hh] = m_rna(dtv[2 * i + hh]);
+                    }
+            }
+    }
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+        const float* Wf = Wn + net * chain_net_floats(KS1, NH, NO);
+        const float* Wb = Wt + net * chain_tnet_floats(KS1, NH, NO);
+        if (net == 1) {   // recompute h1, h2 of the t subnet into the buffers
+            uint32_t h[NH][MT][4];
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, KS1, NH>(a1, Wf + chain_w1(KS1, NH, NO), Wf + chain_b1(KS1, NH, NO), lane, acc);
+                c_relu_to_a<MT, NH>(acc, h);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, NH, NH>(h, Wf + chain_w2(KS1, NH, NO), Wf + chain_b2(KS1, NH, NO), lane, acc);
+                c_relu_to_a<MT, NH>(acc, h);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
+        }
+        c_store_afrag<MT, TM, NO>(S + L.go, rp, dout[net]);
+        {
+            uint32_t gh[NH][MT][4];
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, NO, NH>(dout[net], Wb + chain_w3t(KS1, NH, NO), nullptr, lane, acc);
+                c_mask_to_a<MT, TM, NH>(acc, S + L.hb2, rp, gh);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.gb2, rp, gh);
+            {
+                float acc[NH][MT][4];
+                c_layer<false, MT, NH, NH>(gh, Wb + chain_w2t(KS1, NH, NO), nullptr, lane, acc);
+                c_mask_to_a<MT, TM, NH>(acc, S + L.hb1, rp, gh);
+            }
+            c_store_afrag<MT, TM, NH>(S + L.gb1, rp, gh);
+            float da[KS1][MT][4];
+            c_layer<false, MT, NH, KS1>(gh, Wb + chain_w1t(KS1, NH, NO), nullptr, lane, da);
+#pragma unroll
+            for (int j = 0; j < KS1; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int f = 8 * j + 2 * t + c;
+                    if (f < cin) {
+                        float* p = DZ + c_rows<MT, NW>(f < k ? lo + f : d + (f - k), warp, g);
+                        float v[R];
+                        c_ld_rows<MT>(p, v);
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) { v[2 * i] += da[j][i][c]; v[2 * i + 1] += da[j][i][2 + c]; }
+                        c_st_rows<MT>(p, v);
+                    }
+                }
+        }
+        m_cta_sync();
+        float* pn = part + net * chain_dw_net_floats(KS1, NH, NO);
+        c_dw_gemm<MT, NW, NH, NO, false>(S + L.hb2, 0, 0, 0, 0, S + L.go, pn + chain_dw3(KS1, NH, NO), first, warp, lane);
+        c_dw_gemm<MT, NW, NH, NH, false>(S + L.hb1, 0, 0, 0, 0, S + L.gb2, pn + chain_dw2(KS1, NH, NO), first, warp, lane);
+        c_dw_gemm<MT, NW, KS1, NH, true>(XT, lo, k, cin, d, S + L.gb1, pn + chain_dw1(KS1, NH, NO), first, warp, lane);
+        m_cta_sync();
+    }
+}
+
+template <int MT, int NW>
+HINT_DEV void c_node_bwd_dispatch(const ChainNode& nd, int d, float alpha, const float* __restrict__ W, float* S, const ChainBwdSmem& L,
+                                  float* __restrict__ partial, bool first, int warp, int lane) {
+    const float* Wn = W + nd.w_off;
+    const float* Wt = W + nd.wt_off;
+    float* part = partial + nd.dw_off;
+#define HINT_CHAIN_CASE(ID, A, B, C) \
+    case ID: c_node_bwd<MT, NW, A, B, C>(nd.lo, nd.k, nd.cout, nd.cin, d, alpha, Wn, Wt, S, L, part, first, warp, lane); break;
+    switch (nd.shape) {
+        HINT_CHAIN_CASE(0, 1, 1, 1) HINT_CHAIN_CASE(1, 1, 2, 1) HINT_CHAIN_CASE(2, 1, 3, 1) HINT_CHAIN_CASE(3, 1, 5, 1)
+        HINT_CHAIN_CASE(4, 2, 5, 2) HINT_CHAIN_CASE(5, 2, 9, 2) HINT_CHAIN_CASE(6, 3, 9, 3)
+        default: break;
+    }
+#undef HINT_CHAIN_CASE
+}
+
+// CTA-wide tile I/O (all threads): global rows [row0, row0+rows) x width <-> swizzled columns col_base ..
+template <int TM, int NT>
+HINT_DEV void c_load_tile_sw(float* buf, int col_base, const float* __restrict__ gsrc, long long row0, int rows, int width, int tid) {
+    if (width == 0) return;
+    const float* src = gsrc + row0 * width;
+    const int nvalid = rows * width, n = TM * width;
+    for (int i = tid * 4; i < n; i += NT * 4) {
+        float v[4];
+        if (i + 3 < nvalid) {
+#if defined(__CUDA_ARCH__)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(src + i));
+#else
+            for (int e = 0; e < 4; ++e) v[e] = src[i + e];
+#endif
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (i + e < nvalid) ? src[i + e] : 0.f;
+        }
+        int m = i / width, j = i - m * width;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            buf[c_elem<TM>(col_base + j, m)] = v[e];
+            if (++j == width) { j = 0; ++m; }
+        }
+    }
+}
+template <int TM, int NT>
+HINT_DEV void c_store_tile_sw(const float* buf, int col_base, float* __restrict__ gdst, long long row0, int rows, int width, int tid) {
+    if (width == 0) return;
+    float* dst = gdst + row0 * width;
+    const int nvalid = rows * width;
+    for (int i = tid * 4; i < nvalid; i += NT * 4) {
+        float v[4];
+        int m = i / width, j = i - m * width;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = buf[c_elem<TM>(col_base + j, m)];
+            if (++j == width) { j = 0; ++m; }
+        }
+        if (i + 3 < nvalid) {
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+#else
+            for (int e = 0; e < 4; ++e) dst[i + e] = v[e];
+#endif
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i + e < nvalid) dst[i + e] = v[e];
+        }
+    }
+}
+
+template <int MT, int NW>
+HINT_DEV void c_bwd_body(const ChainTables& T, const ChainNode* nodes, const ChainBwdSmem& L, float* S, const float* __restrict__ z,
+                         const float* __restrict__ c, const float* __restrict__ W, const float* __restrict__ dz,
+                         const float* __restrict__ dlogdet, float* __restrict__ x_rec, float* __restrict__ dx, float* __restrict__ dc,
+                         float* __restrict__ partials, long long n_partial, long long B, int tid, int bid, int nblocks) {
+    constexpr int TM = 16 * MT * NW, NT = 32 * NW;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* partial = partials + (long long)bid * n_partial;
+    const long long ntiles = (B + TM - 1) / TM;
+    bool first = true;
+    for (long long tile = bid; tile < ntiles; tile += nblocks) {
+        const long long row0 = tile * TM;
+        const int rows = (int)((B - row0) < TM ? (B - row0) : TM);
+        c_load_tile_sw<TM, NT>(S + L.xt, 0, z, row0, rows, T.d, tid);
+        c_load_tile_sw<TM, NT>(S + L.xt, T.d, c, row0, rows, T.dc, tid);
+        c_load_tile_sw<TM, NT>(S + L.dz, 0, dz, row0, rows, T.d, tid);
+        for (int i = tid; i < T.dc * TM; i += NT) S[L.dz + (T.d + i / TM) * TM + (i % TM)] = 0.f;
+        for (int i = tid; i < TM; i += NT) S[L.dj + i] = (i < rows) ? dlogdet[row0 + i] : 0.f;
+        m_cta_sync();
+        for (int q = T.n_nodes - 1; q >= 0; --q)
+            c_node_bwd_dispatch<MT, NW>(nodes[q], T.d, T.alpha, W, S, L, partial, first, warp, lane);
+        if (x_rec) c_store_tile_sw<TM, NT>(S + L.xt, 0, x_rec, row0, rows, T.d, tid);
+        c_store_tile_sw<TM, NT>(S + L.dz, 0, dx, row0, rows, T.d, tid);
+        if (dc) c_store_tile_sw<TM, NT>(S + L.dz, T.d, dc, row0, rows, T.dc, tid);
+        m_cta_sync();
+        first = false;
+    }
+}
+
+#if defined(__CUDACC__)
+template <int MT, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+hint_bwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_constant__ ChainParam P, const __grid_constant__ ChainBwdSmem L,
+                      const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ W,
+                      const float* __restrict__ dz, const float* __restrict__ dlogdet, float* __restrict__ x_rec,
+                      float* __restrict__ dx, float* __restrict__ dc, float* __restrict__ partials, long long n_partial, long long B) {
+    extern __shared__ float4 c_smem4[];
+    float* S = reinterpret_cast<float*>(c_smem4);
+    int* nodes = reinterpret_cast<int*>(S + L.nodes);
+    for (int i = threadIdx.x; i < T.n_nodes * 8; i += 32 * NW) nodes[i] = reinterpret_cast<const int*>(P.nodes)[i];
+    __syncthreads();
+    c_bwd_body<MT, NW>(T, reinterpret_cast<const ChainNode*>(nodes), L, S, z, c, W, dz, dlogdet, x_rec, dx, dc, partials, n_partial, B,
+                       threadIdx.x, blockIdx.x, gridDim.x);
+}
+#endif
+
 }  // namespace hint

@@ -42,6 +42,31 @@ FwdCfg pick_fwd(const Plan& p, const ChainPlan& c) {
     return FwdCfg{1, 16, 0, fwd_smem(p, c, 1, 16, 0)};
 }
 
+// backward configuration: (MT, NW) = (1, 4) with two CTAs per SM, or (1, 8) / (2, 4) with one; HINT_B200_CHAIN_BWD=<mt><nw>
+struct BwdCfg { int mt, nw; };
+BwdCfg pick_bwd() {
+    static const char* e = std::getenv("HINT_B200_CHAIN_BWD");
+    if (e && e[0] && e[1]) return BwdCfg{e[0] - '0', e[1] - '0'};
+    return BwdCfg{1, 4};
+}
+ChainBwdSmem bwd_layout(const Plan& p, const ChainPlan& c, BwdCfg b) {
+    if (b.mt == 1 && b.nw == 4) return chain_bwd_smem<1, 4>(p.d, p.dc, c.max_nh, c.max_no, c.n_nodes);
+    if (b.mt == 1 && b.nw == 8) return chain_bwd_smem<1, 8>(p.d, p.dc, c.max_nh, c.max_no, c.n_nodes);
+    return chain_bwd_smem<2, 4>(p.d, p.dc, c.max_nh, c.max_no, c.n_nodes);
+}
+template <int MT, int NW, int MINB>
+cudaError_t setup_bwd(size_t smem, int num_sms, int* ctas) {
+    const void* fn = (const void*)hint_bwd_chain_kernel<MT, NW, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * NW, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    *ctas = occ * num_sms;
+    return cudaSuccess;
+}
+
 template <typename T>
 cudaError_t upload(T** dst, const std::vector<T>& v) {
     *dst = nullptr;
@@ -65,6 +90,14 @@ cudaError_t chain_setup(const Plan& p, const ChainPlan& c, int num_sms, DevChain
     if ((e = set_attr<1, 16, false>()) != cudaSuccess) return e;
     if ((e = set_attr<2, 8, true>()) != cudaSuccess) return e;
     if ((e = set_attr<2, 8, false>()) != cudaSuccess) return e;
+    const BwdCfg b = pick_bwd();
+    d.bwd_mt = b.mt; d.bwd_nw = b.nw;
+    d.bwd_smem = (size_t)bwd_layout(p, c, b).total * 4;
+    if (d.bwd_smem > (size_t)kSmemMax) return cudaErrorInvalidValue;
+    if (b.mt == 1 && b.nw == 4) e = setup_bwd<1, 4, 2>(d.bwd_smem, num_sms, &d.bwd_ctas);
+    else if (b.mt == 1 && b.nw == 8) e = setup_bwd<1, 8, 1>(d.bwd_smem, num_sms, &d.bwd_ctas);
+    else e = setup_bwd<2, 4, 1>(d.bwd_smem, num_sms, &d.bwd_ctas);
+    if (e != cudaSuccess) return e;
     if ((e = upload(&d.pack_src, c.pack_src)) != cudaSuccess) return e;
     return upload(&d.unpack_src, c.unpack_src);
 }
@@ -79,6 +112,29 @@ cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* param
     const int threads = 256;
     const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
     hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, nullptr, n, 1, 0);
+    return cudaGetLastError();
+}
+
+int chain_bwd_ctas(const ChainPlan& c, const DevChain& d, long long B) {
+    (void)c;
+    const int TM = 16 * d.bwd_mt * d.bwd_nw;
+    const long long ntiles = (B + TM - 1) / TM;
+    return (int)std::min<long long>(ntiles, d.bwd_ctas);
+}
+
+cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& d, int grid, const float* z, const float* cond,
+                             const float* packed, const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc,
+                             float* partials, long long B, cudaStream_t st) {
+    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed};
+    const BwdCfg b{d.bwd_mt, d.bwd_nw};
+    const ChainBwdSmem L = bwd_layout(p, c, b);
+    const long long np = c.n_partial;
+    if (b.mt == 1 && b.nw == 4)
+        hint_bwd_chain_kernel<1, 4, 2><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
+    else if (b.mt == 1 && b.nw == 8)
+        hint_bwd_chain_kernel<1, 8, 1><<<grid, 256, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
+    else
+        hint_bwd_chain_kernel<2, 4, 1><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
     return cudaGetLastError();
 }
 

@@ -114,18 +114,18 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                 }
                 set_exact(chain_b3(KS1, NH, NO) + r, b3 + r);
             }
-            // partial gradients: dW_l as C fragments, M = out features, N = in features with the bias in column K_l
+            // partial gradients: dW_lT = [In | 1]^T dOut as C fragments (rows = in features, bias row 8*k_tiles8)
             const int64_t dbase = dw_off[i] + (int64_t)net * chain_dw_net_floats(KS1, NH, NO);
             auto un = [&](int64_t param, int64_t idx) { c.unpack_src[(size_t)param] = (int32_t)(dbase + idx); };
             for (int u = 0; u < nd.h; ++u) {
-                for (int f = 0; f < nd.cin; ++f) un(w1 + (int64_t)u * nd.cin + f, chain_dw1(KS1, NH, NO) + cfrag(chain_dw_nt(KS1), u, f));
-                un(b1 + u, chain_dw1(KS1, NH, NO) + cfrag(chain_dw_nt(KS1), u, 8 * KS1));
-                for (int v = 0; v < nd.h; ++v) un(w2 + (int64_t)u * nd.h + v, chain_dw2(KS1, NH, NO) + cfrag(chain_dw_nt(NH), u, v));
-                un(b2 + u, chain_dw2(KS1, NH, NO) + cfrag(chain_dw_nt(NH), u, 8 * NH));
+                for (int f = 0; f < nd.cin; ++f) un(w1 + (int64_t)u * nd.cin + f, chain_dw1(KS1, NH, NO) + cfrag(NH, f, u));
+                un(b1 + u, chain_dw1(KS1, NH, NO) + cfrag(NH, 8 * KS1, u));
+                for (int v = 0; v < nd.h; ++v) un(w2 + (int64_t)u * nd.h + v, chain_dw2(KS1, NH, NO) + cfrag(NH, v, u));
+                un(b2 + u, chain_dw2(KS1, NH, NO) + cfrag(NH, 8 * NH, u));
             }
             for (int r = 0; r < nd.cout; ++r) {
-                for (int v = 0; v < nd.h; ++v) un(w3 + (int64_t)r * nd.h + v, chain_dw3(KS1, NH, NO) + cfrag(chain_dw_nt(NH), r, v));
-                un(b3 + r, chain_dw3(KS1, NH, NO) + cfrag(chain_dw_nt(NH), r, 8 * NH));
+                for (int v = 0; v < nd.h; ++v) un(w3 + (int64_t)r * nd.h + v, chain_dw3(KS1, NH, NO) + cfrag(NO, v, r));
+                un(b3 + r, chain_dw3(KS1, NH, NO) + cfrag(NO, 8 * NH, r));
             }
         }
     }

@@ -54,15 +54,14 @@ HINT_HD constexpr int chain_w2t(int, int nh, int no) { return no * nh * 64; }
 HINT_HD constexpr int chain_w1t(int ks1, int nh, int no) { return chain_w2t(ks1, nh, no) + nh * nh * 64; }
 HINT_HD constexpr int chain_tnet_floats(int ks1, int nh, int no) { return chain_w1t(ks1, nh, no) + nh * ks1 * 64; }
 
-// Partial-gradient block of one node = two nets, each [dW1 | dW2 | dW3] where dW_l is stored as C fragments:
-// (m-tile over OUT features, n-tile over IN features incl. the bias column, lane, 4 floats)
-// out rows padded to 16, in-features + 1 (bias) padded to 8.
-HINT_HD constexpr int chain_dw_mt(int n_tiles8) { return (n_tiles8 + 1) / 2; }            // 16-row m-tiles covering n_tiles8*8 rows
-HINT_HD constexpr int chain_dw_nt(int k_tiles8) { return k_tiles8 + 1; }                   // n-tiles covering 8*k_tiles8 features + bias
+// Partial-gradient block of one node = two nets, each [dW1T | dW2T | dW3T] where dW_lT = [In | 1]^T * dOut is stored as the
+// C fragments of that product: (m-tile over IN features, the bias row at index 8*k_tiles8 right after the padded features;
+// n-tile over OUT features; lane; 4 floats).
+HINT_HD constexpr int chain_dw_mt(int k_tiles8) { return (8 * k_tiles8 + 1 + 15) / 16; }
 HINT_HD constexpr int chain_dw1(int, int, int) { return 0; }
-HINT_HD constexpr int chain_dw2(int ks1, int nh, int) { return chain_dw_mt(nh) * chain_dw_nt(ks1) * 128; }
-HINT_HD constexpr int chain_dw3(int ks1, int nh, int no) { return chain_dw2(ks1, nh, no) + chain_dw_mt(nh) * chain_dw_nt(nh) * 128; }
-HINT_HD constexpr int chain_dw_net_floats(int ks1, int nh, int no) { return chain_dw3(ks1, nh, no) + chain_dw_mt(no) * chain_dw_nt(nh) * 128; }
+HINT_HD constexpr int chain_dw2(int ks1, int nh, int) { return chain_dw_mt(ks1) * nh * 128; }
+HINT_HD constexpr int chain_dw3(int ks1, int nh, int no) { return chain_dw2(ks1, nh, no) + chain_dw_mt(nh) * nh * 128; }
+HINT_HD constexpr int chain_dw_net_floats(int ks1, int nh, int no) { return chain_dw3(ks1, nh, no) + chain_dw_mt(nh) * no * 128; }
 
 struct ChainNode {      // device-visible, 32 bytes
     int shape;          // index into kChainShapes

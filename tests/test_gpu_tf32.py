@@ -136,7 +136,7 @@ def test_golden_3xtf32_full_parity(golden):
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c[0])
-@pytest.mark.parametrize("mode,tol", [("tf32", 2e-2), ("tf32x3", 1e-4)])
+@pytest.mark.parametrize("mode,tol", [("tf32", 2e-2), ("tf32x3", 2e-4)])
 def test_backward_tensor_core_modes(cfg, mode, tol):
     """Backward of the warp-MMA kernels against the fp64 oracle on the reference configs (relative L2 error of dx, dc and the
     flat parameter gradient; single-pass TF32 bound 2e-2: ReLU kinks make a few samples flip, see test_gpu_parity.py)."""
