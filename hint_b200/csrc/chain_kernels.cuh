@@ -114,6 +114,27 @@ HINT_DEV void c_layer(const uint32_t (&a)[KS][MT][4], const float* __restrict__ 
     }
 }
 
+// block-diagonal layer (super node): n-tile j only sees k-step j; the operand holds the NT diagonal fragments
+template <bool WS, int MT, int NT>
+HINT_DEV void c_layer_bd(const uint32_t (&a)[NT][MT][4], const float* __restrict__ Wl, const float* __restrict__ bl, int lane,
+                         float (&acc)[NT][MT][4]) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float b0 = 0.f, b1 = 0.f, w0, w1;
+        if (bl != nullptr) c_ldw2<WS>(bl + 8 * j + 2 * t, b0, b1);
+        c_ldw2<WS>(Wl + j * 64 + 2 * lane, w0, w1);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[j][i], m_bits(w0), m_bits(w1), b0, b1);
+    }
+}
+template <bool WS, int MT, int NT, int BD>
+HINT_DEV void c_layer_hh(const uint32_t (&a)[NT][MT][4], const float* __restrict__ Wl, const float* __restrict__ bl, int lane,
+                         float (&acc)[NT][MT][4]) {
+    if (BD) c_layer_bd<WS, MT, NT>(a, Wl, bl, lane, acc);
+    else c_layer<WS, MT, NT, NT>(a, Wl, bl, lane, acc);
+}
+
 // C fragments -> A fragments of the next layer (k-slot permutation: a = {c0, c2, c1, c3}), ReLU and tf32 rounding in place
 template <int MT, int NT>
 HINT_DEV void c_relu_to_a(const float (&acc)[NT][MT][4], uint32_t (&a)[NT][MT][4]) {
@@ -126,63 +147,64 @@ HINT_DEV void c_relu_to_a(const float (&acc)[NT][MT][4], uint32_t (&a)[NT][MT][4
         }
 }
 
-// layer-1 A fragments from the warp's x tile: input feature f < k is x column lo+f, k <= f < cin the condition column
-// d + (f - k), beyond that zero (the packed W1 rows are zero there too)
+// layer-1 A fragments from the warp's x tile: input feature f reads tile column in_col[f] (x column, or d + j for
+// condition column j); -1 = no such feature (zero; the packed W1 rows are zero there too)
 template <int MT, int KS1>
-HINT_DEV void c_load_input(const float* XT, int lo, int k, int cin, int d, int lane, uint32_t (&a)[KS1][MT][4]) {
+HINT_DEV void c_load_input(const float* XT, const short* in_col, int lane, uint32_t (&a)[KS1][MT][4]) {
     constexpr int PW = 16 * MT + 4, R = 2 * MT;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int ks = 0; ks < KS1; ++ks)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int f = 8 * ks + 2 * t + c;
+            const int col = in_col[8 * ks + 2 * t + c];
             float v[R];
 #pragma unroll
             for (int e = 0; e < R; ++e) v[e] = 0.f;
-            if (f < cin) c_ld_rows<MT>(XT + (f < k ? lo + f : d + (f - k)) * PW + R * g, v);
+            if (col >= 0) c_ld_rows<MT>(XT + col * PW + R * g, v);
 #pragma unroll
             for (int i = 0; i < MT; ++i) { a[ks][i][2 * c] = m_rna(v[2 * i]); a[ks][i][2 * c + 1] = m_rna(v[2 * i + 1]); }
         }
 }
 
-// s / t subnet of one node (hint.py:10-13,77) entirely in registers
-template <bool WS, int MT, int KS1, int NH, int NO>
+// s / t subnet of one (super) node (hint.py:10-13,77) entirely in registers
+template <bool WS, int MT, int KS1, int NH, int NO, int BD>
 HINT_DEV void c_subnet(const uint32_t (&a1)[KS1][MT][4], const float* __restrict__ Wnet, int lane, float (&out)[NO][MT][4]) {
+    using O = ChainOff<KS1, NH, NO, BD>;
     uint32_t h[NH][MT][4];
     {
         float acc[NH][MT][4];
-        c_layer<WS, MT, KS1, NH>(a1, Wnet + chain_w1(KS1, NH, NO), Wnet + chain_b1(KS1, NH, NO), lane, acc);
+        c_layer<WS, MT, KS1, NH>(a1, Wnet + O::w1, Wnet + O::b1, lane, acc);
         c_relu_to_a<MT, NH>(acc, h);
     }
     {
         float acc[NH][MT][4];
-        c_layer<WS, MT, NH, NH>(h, Wnet + chain_w2(KS1, NH, NO), Wnet + chain_b2(KS1, NH, NO), lane, acc);
+        c_layer_hh<WS, MT, NH, BD>(h, Wnet + O::w2, Wnet + O::b2, lane, acc);
         c_relu_to_a<MT, NH>(acc, h);
     }
-    c_layer<WS, MT, NH, NO>(h, Wnet + chain_w3(KS1, NH, NO), Wnet + chain_b3(KS1, NH, NO), lane, out);
+    c_layer<WS, MT, NH, NO>(h, Wnet + O::w3, Wnet + O::b3, lane, out);
 }
 
-// one tree node, forward (hint.py:79-81) or inverse (hint.py:82-84) coupling; JP = the lane's private log-det partials
-template <bool WS, int MT, int KS1, int NH, int NO, bool REV>
-HINT_DEV void c_node_fwd(int lo, int k, int cout, int cin, int d, float alpha, const float* __restrict__ Wn, float* XT, float* JP,
-                         int lane) {
+// one (super) node, forward (hint.py:79-81) or inverse (hint.py:82-84) coupling; JP = the lane's private log-det partials
+template <bool WS, int MT, int KS1, int NH, int NO, int BD, bool REV>
+HINT_DEV void c_node_fwd(const ChainNode* nd, float alpha, const float* __restrict__ Wn, float* XT, float* JP, int lane) {
     constexpr int PW = 16 * MT + 4, R = 2 * MT;
+    using O = ChainOff<KS1, NH, NO, BD>;
     const int g = lane >> 2, t = lane & 3;
     uint32_t a1[KS1][MT][4];
-    c_load_input<MT, KS1>(XT, lo, k, cin, d, lane, a1);
+    c_load_input<MT, KS1>(XT, nd->in_col, lane, a1);
     float s[NO][MT][4], tt[NO][MT][4];
-    c_subnet<WS, MT, KS1, NH, NO>(a1, Wn, lane, s);
-    c_subnet<WS, MT, KS1, NH, NO>(a1, Wn + chain_net_floats(KS1, NH, NO), lane, tt);
+    c_subnet<WS, MT, KS1, NH, NO, BD>(a1, Wn, lane, s);
+    c_subnet<WS, MT, KS1, NH, NO, BD>(a1, Wn + O::net, lane, tt);
     float jl[R];
     c_ld_rows<MT>(JP + (t * 16 * MT) + R * g, jl);
 #pragma unroll
     for (int j = 0; j < NO; ++j)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int col = 8 * j + 2 * t + c;
-            if (col < cout) {
-                float* xp = XT + (lo + k + col) * PW + R * g;
+            const int xcol = nd->out_col[8 * j + 2 * t + c];
+            if (xcol >= 0) {
+                float* xp = XT + xcol * PW + R * g;
                 float xv[R];
                 c_ld_rows<MT>(xp, xv);
 #pragma unroll
@@ -201,14 +223,16 @@ HINT_DEV void c_node_fwd(int lo, int k, int cout, int cin, int d, float alpha, c
     c_st_rows<MT>(JP + (t * 16 * MT) + R * g, jl);
 }
 
+#define HINT_CHAIN_SHAPES(X) X(0, 1, 1, 1, 0) X(1, 1, 2, 1, 1) X(2, 1, 4, 1, 1) X(3, 1, 2, 1, 0) X(4, 1, 3, 1, 0) \
+                             X(5, 1, 5, 1, 0) X(6, 2, 5, 2, 0) X(7, 2, 9, 2, 0) X(8, 3, 9, 3, 0)
+
 template <bool WS, int MT, bool REV>
-HINT_DEV void c_node_fwd_dispatch(const ChainNode& nd, int d, float alpha, const float* __restrict__ W, float* XT, float* JP, int lane) {
-    const float* Wn = W + nd.w_off;
-#define HINT_CHAIN_CASE(ID, A, B, C) \
-    case ID: c_node_fwd<WS, MT, A, B, C, REV>(nd.lo, nd.k, nd.cout, nd.cin, d, alpha, Wn, XT, JP, lane); break;
-    switch (nd.shape) {
-        HINT_CHAIN_CASE(0, 1, 1, 1) HINT_CHAIN_CASE(1, 1, 2, 1) HINT_CHAIN_CASE(2, 1, 3, 1) HINT_CHAIN_CASE(3, 1, 5, 1)
-        HINT_CHAIN_CASE(4, 2, 5, 2) HINT_CHAIN_CASE(5, 2, 9, 2) HINT_CHAIN_CASE(6, 3, 9, 3)
+HINT_DEV void c_node_fwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* XT, float* JP, int lane) {
+    const float* Wn = W + nd->w_off;
+#define HINT_CHAIN_CASE(ID, A, B, C, D) \
+    case ID: c_node_fwd<WS, MT, A, B, C, D, REV>(nd, alpha, Wn, XT, JP, lane); break;
+    switch (nd->shape) {
+        HINT_CHAIN_SHAPES(HINT_CHAIN_CASE)
         default: break;
     }
 #undef HINT_CHAIN_CASE
@@ -291,8 +315,7 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
         for (int i = lane; i < 4 * RW; i += 32) JP[i] = 0.f;
         c_syncwarp();
         for (int q = 0; q < T.n_nodes; ++q) {
-            const ChainNode& nd = nodes[REV ? T.n_nodes - 1 - q : q];
-            c_node_fwd_dispatch<WS, MT, REV>(nd, T.d, T.alpha, W, XT, JP, lane);
+            c_node_fwd_dispatch<WS, MT, REV>(nodes + (REV ? T.n_nodes - 1 - q : q), T.alpha, W, XT, JP, lane);
             c_syncwarp();
         }
         c_store_tile<MT>(XT, 0, z, row0, rows, T.d, lane);
@@ -302,7 +325,7 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
 }
 
 // shared memory of the forward kernels: [node table | forward operands (WS only) | NW warp tiles]
-HINT_HD constexpr int chain_node_floats(int n_nodes) { return n_nodes * 8; }
+HINT_HD constexpr int chain_node_floats(int n_nodes) { return n_nodes * 32; }
 template <int MT>
 HINT_HD constexpr size_t chain_fwd_smem_bytes(int n_nodes, int d, int dc, int nw, long long n_fwd_packed, bool ws) {
     return 4 * ((size_t)chain_node_floats(n_nodes) + (ws ? (size_t)n_fwd_packed : 0) + (size_t)nw * chain_fwd_warp_floats<MT>(d, dc));
@@ -319,7 +342,7 @@ hint_fwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
     extern __shared__ float4 c_smem4[];
     float* S = reinterpret_cast<float*>(c_smem4);
     int* nodes = reinterpret_cast<int*>(S);
-    for (int i = threadIdx.x; i < T.n_nodes * 8; i += 32 * NW) nodes[i] = reinterpret_cast<const int*>(P.nodes)[i];
+    for (int i = threadIdx.x; i < T.n_nodes * 32; i += 32 * NW) nodes[i] = reinterpret_cast<const int*>(P.nodes)[i];
     float* Ws = S + chain_node_floats(T.n_nodes);
     if (WS) {
         const float4* src = reinterpret_cast<const float4*>(W);
@@ -379,23 +402,23 @@ HINT_HD constexpr ChainBwdSmem chain_bwd_smem(int d, int dc, int max_nh, int max
     s.go = s.gb2 + 8 * max_nh * TM;
     s.dj = s.go + 8 * max_no * TM;
     s.nodes = s.dj + TM;
-    s.total = s.nodes + 8 * n_nodes;
+    s.total = s.nodes + 32 * n_nodes;
     return s;
 }
 
 template <int MT, int NW, int KS1>
-HINT_DEV void c_load_input_sw(const float* XT, int lo, int k, int cin, int d, int warp, int lane, uint32_t (&a)[KS1][MT][4]) {
+HINT_DEV void c_load_input_sw(const float* XT, const short* in_col, int warp, int lane, uint32_t (&a)[KS1][MT][4]) {
     constexpr int R = 2 * MT;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int ks = 0; ks < KS1; ++ks)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int f = 8 * ks + 2 * t + c;
+            const int col = in_col[8 * ks + 2 * t + c];
             float v[R];
 #pragma unroll
             for (int e = 0; e < R; ++e) v[e] = 0.f;
-            if (f < cin) c_ld_rows<MT>(XT + c_rows<MT, NW>(f < k ? lo + f : d + (f - k), warp, g), v);
+            if (col >= 0) c_ld_rows<MT>(XT + c_rows<MT, NW>(col, warp, g), v);
 #pragma unroll
             for (int i = 0; i < MT; ++i) { a[ks][i][2 * c] = m_rna(v[2 * i]); a[ks][i][2 * c + 1] = m_rna(v[2 * i + 1]); }
         }
@@ -438,16 +461,17 @@ HINT_DEV void c_mask_to_a(const float (&acc)[NT][MT][4], const float* hbuf, cons
 
 // weight-gradient GEMM of one layer: CT[in-feature rows | ones row][out cols] += sum over the tile's samples.
 //   XIN: the in-features are the node's subnet inputs (x_upper' / condition columns of the x tile), else columns of `abuf`.
+//   rot: rotates the unit -> warp assignment so that the small GEMMs of one phase land on different warps
 template <int MT, int NW, int KSIN, int NTOUT, bool XIN>
-HINT_DEV void c_dw_gemm(const float* abuf, int lo, int k, int cin, int d, const float* bbuf, float* __restrict__ part, bool first,
-                        int warp, int lane) {
+HINT_DEV void c_dw_gemm(const float* abuf, const short* in_col, const float* bbuf, float* __restrict__ part, bool first,
+                        int warp, int lane, int rot) {
     constexpr int TM = 16 * MT * NW;
-    constexpr int MTC = chain_dw_mt(KSIN);
+    constexpr int MTC = (8 * KSIN + 1 + 15) / 16;
     constexpr int NC = NTOUT <= 5 ? NTOUT : 3;
     constexpr int NCH = NTOUT / NC;
     static_assert(NCH * NC == NTOUT, "n-chunking must tile the layer");
     const int g = lane >> 2, t = lane & 3;
-    for (int u = warp; u < MTC * NCH; u += NW) {
+    for (int u = (warp + NW - rot) % NW; u < MTC * NCH; u += NW) {
         const int i = u / NCH, ch = u - i * NCH;
         // A rows r0 = 16i + g, r1 = r0 + 8: feature column, the ones row (bias) or zero padding
         int abase[2], amode[2];      // amode 0 load, 1 ones, 2 zero
@@ -457,7 +481,7 @@ HINT_DEV void c_dw_gemm(const float* abuf, int lo, int k, int cin, int d, const 
             int col = 0;
             amode[hh] = 0;
             if (XIN) {
-                if (r < cin) col = r < k ? lo + r : d + (r - k);
+                if (r < 8 * KSIN) { col = in_col[r]; if (col < 0) { col = 0; amode[hh] = 2; } }
                 else amode[hh] = (r == 8 * KSIN) ? 1 : 2;
             } else {
                 if (r < 8 * KSIN) col = r;
@@ -533,11 +557,12 @@ HINT_DEV void c_dw_gemm(const float* abuf, int lo, int k, int cin, int d, const 
     }
 }
 
-// one tree node of the backward sweep
-template <int MT, int NW, int KS1, int NH, int NO>
-HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, const float* __restrict__ Wn, const float* __restrict__ Wt,
+// one (super) node of the backward sweep
+template <int MT, int NW, int KS1, int NH, int NO, int BD>
+HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restrict__ Wn, const float* __restrict__ Wt,
                          float* S, const ChainBwdSmem& L, float* __restrict__ part, bool first, int warp, int lane) {
     constexpr int TM = 16 * MT * NW, R = 2 * MT;
+    using O = ChainOff<KS1, NH, NO, BD>;
     const int g = lane >> 2, t = lane & 3;
     float* XT = S + L.xt;
     float* DZ = S + L.dz;
@@ -546,26 +571,26 @@ HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, c
     rp[0] = c_rows<MT, NW>(2 * t, warp, g);
     rp[1] = c_rows<MT, NW>(2 * t + 1, warp, g);
     uint32_t a1[KS1][MT][4];
-    c_load_input_sw<MT, NW, KS1>(XT, lo, k, cin, d, warp, lane, a1);
-    uint32_t dout[2][NO][MT][4];      // ds, dt as A fragments
+    c_load_input_sw<MT, NW, KS1>(XT, nd->in_col, warp, lane, a1);
+    uint32_t ds[NO][MT][4], dt[NO][MT][4];      // ds, dt as A fragments
     {
         float s[NO][MT][4], tt[NO][MT][4];
-        c_subnet<false, MT, KS1, NH, NO>(a1, Wn + chain_net_floats(KS1, NH, NO), lane, tt);
+        c_subnet<false, MT, KS1, NH, NO, BD>(a1, Wn + O::net, lane, tt);
         {   // s subnet, keeping h1 / h2 in the CTA-wide buffers
             uint32_t h[NH][MT][4];
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, KS1, NH>(a1, Wn + chain_w1(KS1, NH, NO), Wn + chain_b1(KS1, NH, NO), lane, acc);
+                c_layer<false, MT, KS1, NH>(a1, Wn + O::w1, Wn + O::b1, lane, acc);
                 c_relu_to_a<MT, NH>(acc, h);
             }
             c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, NH, NH>(h, Wn + chain_w2(KS1, NH, NO), Wn + chain_b2(KS1, NH, NO), lane, acc);
+                c_layer_hh<false, MT, NH, BD>(h, Wn + O::w2, Wn + O::b2, lane, acc);
                 c_relu_to_a<MT, NH>(acc, h);
             }
             c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
-            c_layer<false, MT, NH, NO>(h, Wn + chain_w3(KS1, NH, NO), Wn + chain_b3(KS1, NH, NO), lane, s);
+            c_layer<false, MT, NH, NO>(h, Wn + O::w3, Wn + O::b3, lane, s);
         }
         // coupling backward on the C fragments
         float dj[R];
@@ -574,12 +599,12 @@ HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, c
         for (int j = 0; j < NO; ++j)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int col = 8 * j + 2 * t + c;
+                const int xcol = nd->out_col[8 * j + 2 * t + c];
                 float dsv[R], dtv[R];
 #pragma unroll
                 for (int e = 0; e < R; ++e) { dsv[e] = 0.f; dtv[e] = 0.f; }
-                if (col < cout) {
-                    const int ra = c_rows<MT, NW>(lo + k + col, warp, g);
+                if (xcol >= 0) {
+                    const int ra = c_rows<MT, NW>(xcol, warp, g);
                     float zl[R], dzl[R];
                     c_ld_rows<MT>(XT + ra, zl);
                     c_ld_rows<MT>(DZ + ra, dzl);
@@ -603,54 +628,61 @@ HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, c
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        dout[0][j][i][2 * c + hh] = m_rna(dsv[2 * i + hh]);
-                        dout[1][j][i][2 * c + hh] = m_rna(dtv[2 * i + hh]);
+                        ds[j][i][2 * c + hh] = m_rna(dsv[2 * i + hh]);
+                        dt[j][i][2 * c + hh] = m_rna(dtv[2 * i + hh]);
                     }
             }
     }
-#pragma unroll
+#pragma unroll 1
     for (int net = 0; net < 2; ++net) {
-        const float* Wf = Wn + net * chain_net_floats(KS1, NH, NO);
-        const float* Wb = Wt + net * chain_tnet_floats(KS1, NH, NO);
+        const float* Wf = Wn + net * O::net;
+        const float* Wb = Wt + net * O::tnet;
+        uint32_t dout[NO][MT][4];
+#pragma unroll
+        for (int j = 0; j < NO; ++j)
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dout[j][i][e] = net ? dt[j][i][e] : ds[j][i][e];
         if (net == 1) {   // recompute h1, h2 of the t subnet into the buffers
             uint32_t h[NH][MT][4];
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, KS1, NH>(a1, Wf + chain_w1(KS1, NH, NO), Wf + chain_b1(KS1, NH, NO), lane, acc);
+                c_layer<false, MT, KS1, NH>(a1, Wf + O::w1, Wf + O::b1, lane, acc);
                 c_relu_to_a<MT, NH>(acc, h);
             }
             c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, NH, NH>(h, Wf + chain_w2(KS1, NH, NO), Wf + chain_b2(KS1, NH, NO), lane, acc);
+                c_layer_hh<false, MT, NH, BD>(h, Wf + O::w2, Wf + O::b2, lane, acc);
                 c_relu_to_a<MT, NH>(acc, h);
             }
             c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
         }
-        c_store_afrag<MT, TM, NO>(S + L.go, rp, dout[net]);
+        c_store_afrag<MT, TM, NO>(S + L.go, rp, dout);
         {
             uint32_t gh[NH][MT][4];
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, NO, NH>(dout[net], Wb + chain_w3t(KS1, NH, NO), nullptr, lane, acc);
+                c_layer<false, MT, NO, NH>(dout, Wb + O::w3t, nullptr, lane, acc);
                 c_mask_to_a<MT, TM, NH>(acc, S + L.hb2, rp, gh);
             }
             c_store_afrag<MT, TM, NH>(S + L.gb2, rp, gh);
             {
                 float acc[NH][MT][4];
-                c_layer<false, MT, NH, NH>(gh, Wb + chain_w2t(KS1, NH, NO), nullptr, lane, acc);
+                c_layer_hh<false, MT, NH, BD>(gh, Wb + O::w2t, nullptr, lane, acc);
                 c_mask_to_a<MT, TM, NH>(acc, S + L.hb1, rp, gh);
             }
             c_store_afrag<MT, TM, NH>(S + L.gb1, rp, gh);
             float da[KS1][MT][4];
-            c_layer<false, MT, NH, KS1>(gh, Wb + chain_w1t(KS1, NH, NO), nullptr, lane, da);
+            c_layer<false, MT, NH, KS1>(gh, Wb + O::w1t, nullptr, lane, da);
 #pragma unroll
             for (int j = 0; j < KS1; ++j)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int f = 8 * j + 2 * t + c;
-                    if (f < cin) {
-                        float* p = DZ + c_rows<MT, NW>(f < k ? lo + f : d + (f - k), warp, g);
+                    const int col = nd->in_col[8 * j + 2 * t + c];
+                    if (col >= 0) {
+                        float* p = DZ + c_rows<MT, NW>(col, warp, g);
                         float v[R];
                         c_ld_rows<MT>(p, v);
 #pragma unroll
@@ -660,25 +692,25 @@ HINT_DEV void c_node_bwd(int lo, int k, int cout, int cin, int d, float alpha, c
                 }
         }
         m_cta_sync();
-        float* pn = part + net * chain_dw_net_floats(KS1, NH, NO);
-        c_dw_gemm<MT, NW, NH, NO, false>(S + L.hb2, 0, 0, 0, 0, S + L.go, pn + chain_dw3(KS1, NH, NO), first, warp, lane);
-        c_dw_gemm<MT, NW, NH, NH, false>(S + L.hb1, 0, 0, 0, 0, S + L.gb2, pn + chain_dw2(KS1, NH, NO), first, warp, lane);
-        c_dw_gemm<MT, NW, KS1, NH, true>(XT, lo, k, cin, d, S + L.gb1, pn + chain_dw1(KS1, NH, NO), first, warp, lane);
+        float* pn = part + net * O::dnet;
+        c_dw_gemm<MT, NW, NH, NO, false>(S + L.hb2, nullptr, S + L.go, pn + O::dw3, first, warp, lane, 0);
+        c_dw_gemm<MT, NW, NH, NH, false>(S + L.hb1, nullptr, S + L.gb2, pn + O::dw2, first, warp, lane, (O::mth * (NO <= 5 ? 1 : NO / 3)) % NW);
+        c_dw_gemm<MT, NW, KS1, NH, true>(XT, nd->in_col, S + L.gb1, pn + O::dw1, first, warp, lane,
+                                         (O::mth * (NO <= 5 ? 1 : NO / 3) + O::mth * (NH <= 5 ? 1 : NH / 3)) % NW);
         m_cta_sync();
     }
 }
 
 template <int MT, int NW>
-HINT_DEV void c_node_bwd_dispatch(const ChainNode& nd, int d, float alpha, const float* __restrict__ W, float* S, const ChainBwdSmem& L,
+HINT_DEV void c_node_bwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* S, const ChainBwdSmem& L,
                                   float* __restrict__ partial, bool first, int warp, int lane) {
-    const float* Wn = W + nd.w_off;
-    const float* Wt = W + nd.wt_off;
-    float* part = partial + nd.dw_off;
-#define HINT_CHAIN_CASE(ID, A, B, C) \
-    case ID: c_node_bwd<MT, NW, A, B, C>(nd.lo, nd.k, nd.cout, nd.cin, d, alpha, Wn, Wt, S, L, part, first, warp, lane); break;
-    switch (nd.shape) {
-        HINT_CHAIN_CASE(0, 1, 1, 1) HINT_CHAIN_CASE(1, 1, 2, 1) HINT_CHAIN_CASE(2, 1, 3, 1) HINT_CHAIN_CASE(3, 1, 5, 1)
-        HINT_CHAIN_CASE(4, 2, 5, 2) HINT_CHAIN_CASE(5, 2, 9, 2) HINT_CHAIN_CASE(6, 3, 9, 3)
+    const float* Wn = W + nd->w_off;
+    const float* Wt = W + nd->wt_off;
+    float* part = partial + nd->dw_off;
+#define HINT_CHAIN_CASE(ID, A, B, C, D) \
+    case ID: c_node_bwd<MT, NW, A, B, C, D>(nd, alpha, Wn, Wt, S, L, part, first, warp, lane); break;
+    switch (nd->shape) {
+        HINT_CHAIN_SHAPES(HINT_CHAIN_CASE)
         default: break;
     }
 #undef HINT_CHAIN_CASE
@@ -757,7 +789,7 @@ HINT_DEV void c_bwd_body(const ChainTables& T, const ChainNode* nodes, const Cha
         for (int i = tid; i < TM; i += NT) S[L.dj + i] = (i < rows) ? dlogdet[row0 + i] : 0.f;
         m_cta_sync();
         for (int q = T.n_nodes - 1; q >= 0; --q)
-            c_node_bwd_dispatch<MT, NW>(nodes[q], T.d, T.alpha, W, S, L, partial, first, warp, lane);
+            c_node_bwd_dispatch<MT, NW>(nodes + q, T.alpha, W, S, L, partial, first, warp, lane);
         if (x_rec) c_store_tile_sw<TM, NT>(S + L.xt, 0, x_rec, row0, rows, T.d, tid);
         c_store_tile_sw<TM, NT>(S + L.dz, 0, dx, row0, rows, T.d, tid);
         if (dc) c_store_tile_sw<TM, NT>(S + L.dz, T.d, dc, row0, rows, T.dc, tid);
@@ -776,7 +808,7 @@ hint_bwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
     extern __shared__ float4 c_smem4[];
     float* S = reinterpret_cast<float*>(c_smem4);
     int* nodes = reinterpret_cast<int*>(S + L.nodes);
-    for (int i = threadIdx.x; i < T.n_nodes * 8; i += 32 * NW) nodes[i] = reinterpret_cast<const int*>(P.nodes)[i];
+    for (int i = threadIdx.x; i < T.n_nodes * 32; i += 32 * NW) nodes[i] = reinterpret_cast<const int*>(P.nodes)[i];
     __syncthreads();
     c_bwd_body<MT, NW>(T, reinterpret_cast<const ChainNode*>(nodes), L, S, z, c, W, dz, dlogdet, x_rec, dx, dc, partials, n_partial, B,
                        threadIdx.x, blockIdx.x, gridDim.x);

@@ -10,10 +10,17 @@
 // constant (a node runs on the smallest instantiated shape that contains it, its operands zero-padded to that shape), so
 // all loops unroll and operand addresses are immediates.
 //
+// Super nodes: most nodes of a HINT tree are tiny (24 of the 31 nodes of the d=43 tree have h = 8, 1-3 inputs and 1-3
+// outputs) and would run one almost empty MMA per layer each.  Up to four adjacent tiny nodes of one tree level (they are
+// independent) are therefore fused into one "super node": their inputs share the single k-step of layer 1, their hidden
+// units are the n-tiles of one block-diagonal layer 2 (only the diagonal fragments are stored and multiplied), and their
+// outputs share ONE n-tile of layer 3 - so the coupling epilogue, the operand loads and every per-node overhead are paid
+// once per group, with the same number of MMAs.  A node is described by two small column maps (input feature -> tile
+// column, output column -> coupled x column), which also cover the ordinary single-node case.
+//
 // Forward / inverse (hint.py:62-101): warps are independent - each owns a tile of 16*MT samples (x columns in a private
-// shared-memory tile [column][sample]) for the whole tree, no CTA barrier anywhere.  Weights are read as B fragments
-// straight from the packed operand buffer through L1 (the buffer is smaller than the L1 that is left).
-// Backward: see the section in chain_kernels.cuh.
+// shared-memory tile [column][sample]) for the whole tree, no CTA barrier anywhere.  Operands are staged in shared memory
+// when they fit next to the tiles, else read through L1.  Backward: see chain_kernels.cuh.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -29,58 +36,66 @@
 
 namespace hint {
 
-constexpr int kChainWarps = 8;
-constexpr int kChainThreads = 32 * kChainWarps;
-constexpr int kChainMaxNodes = 192;
+constexpr int kChainMaxNodes = 128;
+constexpr int kChainMaxIn = 24, kChainMaxOut = 24;    // 8 * max ks1, 8 * max no
 
-// instantiated node shapes: k-steps of layer 1 (8 input features each), n-tiles of the hidden layers, n-tiles of the output
-struct ChainShape { int ks1, nh, no; };
-constexpr int kChainNumShapes = 7;
-constexpr ChainShape kChainShapes[kChainNumShapes] = {{1, 1, 1}, {1, 2, 1}, {1, 3, 1}, {1, 5, 1}, {2, 5, 2}, {2, 9, 2}, {3, 9, 3}};
+// instantiated node shapes: k-steps of layer 1 (8 input features each), n-tiles of the hidden layers, n-tiles of the
+// output, bd = layer 2 is block diagonal with 8x8 blocks (super node of `nh` tiny nodes)
+struct ChainShape { int ks1, nh, no, bd; };
+constexpr int kChainNumShapes = 9;
+constexpr ChainShape kChainShapes[kChainNumShapes] = {{1, 1, 1, 0}, {1, 2, 1, 1}, {1, 4, 1, 1}, {1, 2, 1, 0}, {1, 3, 1, 0},
+                                                      {1, 5, 1, 0}, {2, 5, 2, 0}, {2, 9, 2, 0}, {3, 9, 3, 0}};
 
 // Packed operands.  Forward region (all nodes back to back; small enough to be staged in shared memory by the forward
 // kernel): per node two nets (s, t), each [W1 | b1 | W2 | b2 | W3 | b3].  Transposed region (dgrad GEMMs of the backward),
 // after the forward region: per node two nets, each [W3T | W2T | W1T].
-// W* are B-fragment ordered (k-step major, n-tile, lane, 2 floats), b* natural order.
-HINT_HD constexpr int chain_w1(int, int, int) { return 0; }
-HINT_HD constexpr int chain_b1(int ks1, int nh, int) { return ks1 * nh * 64; }
-HINT_HD constexpr int chain_w2(int ks1, int nh, int no) { return chain_b1(ks1, nh, no) + nh * 8; }
-HINT_HD constexpr int chain_b2(int ks1, int nh, int no) { return chain_w2(ks1, nh, no) + nh * nh * 64; }
-HINT_HD constexpr int chain_w3(int ks1, int nh, int no) { return chain_b2(ks1, nh, no) + nh * 8; }
-HINT_HD constexpr int chain_b3(int ks1, int nh, int no) { return chain_w3(ks1, nh, no) + nh * no * 64; }
-HINT_HD constexpr int chain_net_floats(int ks1, int nh, int no) { return chain_b3(ks1, nh, no) + no * 8; }
-HINT_HD constexpr int chain_w3t(int, int, int) { return 0; }
-HINT_HD constexpr int chain_w2t(int, int nh, int no) { return no * nh * 64; }
-HINT_HD constexpr int chain_w1t(int ks1, int nh, int no) { return chain_w2t(ks1, nh, no) + nh * nh * 64; }
-HINT_HD constexpr int chain_tnet_floats(int ks1, int nh, int no) { return chain_w1t(ks1, nh, no) + nh * ks1 * 64; }
+// W* are B-fragment ordered (k-step major, n-tile, lane, 2 floats; a block-diagonal W2 keeps its nh diagonal fragments),
+// b* natural order.
+template <int KS1, int NH, int NO, int BD>
+struct ChainOff {
+    static constexpr int w2f = (BD ? NH : NH * NH) * 64;
+    static constexpr int w1 = 0, b1 = KS1 * NH * 64, w2 = b1 + NH * 8, b2 = w2 + w2f, w3 = b2 + NH * 8, b3 = w3 + NH * NO * 64;
+    static constexpr int net = b3 + NO * 8;                       // floats of one net in the forward region
+    static constexpr int w3t = 0, w2t = NO * NH * 64, w1t = w2t + w2f;
+    static constexpr int tnet = w1t + NH * KS1 * 64;              // ... in the transposed region
+    // partial gradients of one net: [dW1T | dW2T | dW3T], dW_lT = [In | 1]^T dOut stored as C fragments (m-tile over IN
+    // features with the bias row at index 8*k_tiles right after the padded features, n-tile over OUT features)
+    static constexpr int mt1 = (8 * KS1 + 1 + 15) / 16, mth = (8 * NH + 1 + 15) / 16;
+    static constexpr int dw1 = 0, dw2 = mt1 * NH * 128, dw3 = dw2 + mth * NH * 128;
+    static constexpr int dnet = dw3 + mth * NO * 128;
+};
+struct ChainOffRt { int w1, b1, w2, b2, w3, b3, net, w3t, w2t, w1t, tnet, dw1, dw2, dw3, dnet; };
+inline ChainOffRt chain_off(const ChainShape& s) {
+    ChainOffRt o{};
+    const int w2f = (s.bd ? s.nh : s.nh * s.nh) * 64;
+    o.w1 = 0; o.b1 = s.ks1 * s.nh * 64; o.w2 = o.b1 + s.nh * 8; o.b2 = o.w2 + w2f; o.w3 = o.b2 + s.nh * 8;
+    o.b3 = o.w3 + s.nh * s.no * 64; o.net = o.b3 + s.no * 8;
+    o.w3t = 0; o.w2t = s.no * s.nh * 64; o.w1t = o.w2t + w2f; o.tnet = o.w1t + s.nh * s.ks1 * 64;
+    const int mt1 = (8 * s.ks1 + 1 + 15) / 16, mth = (8 * s.nh + 1 + 15) / 16;
+    o.dw1 = 0; o.dw2 = mt1 * s.nh * 128; o.dw3 = o.dw2 + mth * s.nh * 128; o.dnet = o.dw3 + mth * s.no * 128;
+    return o;
+}
 
-// Partial-gradient block of one node = two nets, each [dW1T | dW2T | dW3T] where dW_lT = [In | 1]^T * dOut is stored as the
-// C fragments of that product: (m-tile over IN features, the bias row at index 8*k_tiles8 right after the padded features;
-// n-tile over OUT features; lane; 4 floats).
-HINT_HD constexpr int chain_dw_mt(int k_tiles8) { return (8 * k_tiles8 + 1 + 15) / 16; }
-HINT_HD constexpr int chain_dw1(int, int, int) { return 0; }
-HINT_HD constexpr int chain_dw2(int ks1, int nh, int) { return chain_dw_mt(ks1) * nh * 128; }
-HINT_HD constexpr int chain_dw3(int ks1, int nh, int no) { return chain_dw2(ks1, nh, no) + chain_dw_mt(nh) * nh * 128; }
-HINT_HD constexpr int chain_dw_net_floats(int ks1, int nh, int no) { return chain_dw3(ks1, nh, no) + chain_dw_mt(nh) * no * 128; }
-
-struct ChainNode {      // device-visible, 32 bytes
+struct ChainNode {      // device-visible, 128 bytes
     int shape;          // index into kChainShapes
-    int lo, k, cout;    // upper half = columns [lo, lo+k), lower half = [lo+k, lo+k+cout)   (hint.py:41,68)
-    int cin;            // k + dc (hint.py:44)
     int w_off;          // float offset of the node's forward operands
     int wt_off;         // float offset of the node's transposed operands
     int dw_off;         // float offset of the node's partial-gradient block
+    short in_col[kChainMaxIn];     // tile column of input feature f: x column, d + j for condition column j, -1 none
+    short out_col[kChainMaxOut];   // x column coupled by output column c (hint.py:79-84), -1 none
+    int pad[4];
 };
+static_assert(sizeof(ChainNode) == 128, "node records are 128 bytes");
 
 struct ChainParam {     // travels as a __grid_constant__ kernel parameter
-    ChainNode nodes[kChainMaxNodes];   // forward order: children before their parent (hint.py:70-73); inverse and
-                                       // backward walk it reversed (hint.py:85-88)
+    ChainNode nodes[kChainMaxNodes];   // forward order: deepest tree level first, so children precede their parent
+                                       // (hint.py:70-73); inverse and backward walk it reversed (hint.py:85-88)
 };
 
 struct ChainPlan {
     bool ok = false;
     std::string why;
-    int n_nodes = 0;
+    int n_nodes = 0;                    // (super) nodes
     ChainParam param;
     int64_t n_packed = 0;               // floats of the whole packed operand buffer
     int64_t n_fwd_packed = 0;           // floats of its forward region (a multiple of 4)
