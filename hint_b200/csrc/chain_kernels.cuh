@@ -13,7 +13,7 @@
 #include "plan_chain.h"
 
 #if !defined(__CUDACC__)
-namespace hint { namespace emu { void warp_sync(); } }
+namespace hint { namespace emu { void warp_sync(); void ldsm4(const float* rowp, uint32_t (&r)[4]); } }
 #endif
 
 namespace hint {
@@ -22,6 +22,8 @@ struct ChainTables {
     int n_nodes, d, dc;
     float alpha;
     int n_fwd_packed;   // floats of the forward operand region (staged in shared memory by the WS kernels)
+    int exp;            // developer experiments (timing only, WRONG results): 1 no partial flush, 2 no dW GEMMs, 4 all operand
+                        // loads hit the first 4 KB of the packed buffer (HINT_B200_CHAIN_EXP)
 };
 
 HINT_DEV void c_syncwarp() {
@@ -74,15 +76,39 @@ HINT_DEV void c_st_rows(float* p, const float (&v)[2 * MT]) {
 #endif
 }
 
-// d = a*b + c with c in its own registers (the bias fragment is shared by all m-tiles: no accumulator initialisation moves)
-HINT_DEV void c_mma_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1) {
+// d = a*b + c with c in its own registers: the bias quad of an n-tile is shared by all its m-tiles, so no accumulator is
+// ever initialised with moves
+HINT_DEV void c_mma_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 #else
-    d[0] = c0; d[1] = c1; d[2] = c0; d[3] = c1;
+    d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
     m_mma(d, a, b0, b1);
+#endif
+}
+// d = a*b (zero accumulator: ptxas encodes the C operand as RZ)
+HINT_DEV void c_mma_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+#else
+    d[0] = d[1] = d[2] = d[3] = 0.f;
+    m_mma(d, a, b0, b1);
+#endif
+}
+// the lane's bias quad of n-tile j: (b[2t], b[2t+1], b[2t], b[2t+1]) stored contiguously
+template <bool WS>
+HINT_DEV void c_ldb4(const float* __restrict__ p, float (&c)[4]) {
+#if defined(__CUDA_ARCH__)
+    float4 v;
+    if (WS) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    else v = __ldg(reinterpret_cast<const float4*>(p));
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+#else
+    for (int e = 0; e < 4; ++e) c[e] = p[e];
 #endif
 }
 
@@ -96,11 +122,17 @@ HINT_DEV void c_layer(const uint32_t (&a)[KS][MT][4], const float* __restrict__ 
     const int t = lane & 3;
 #pragma unroll
     for (int j = 0; j < NT_OUT; ++j) {
-        float b0 = 0.f, b1 = 0.f, w0, w1;
-        if (bl != nullptr) c_ldw2<WS>(bl + 8 * j + 2 * t, b0, b1);
+        float w0, w1;
         c_ldw2<WS>(Wl + j * 64 + 2 * lane, w0, w1);
+        if (bl != nullptr) {
+            float bq[4];
+            c_ldb4<WS>(bl + 16 * j + 4 * t, bq);
 #pragma unroll
-        for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[0][i], m_bits(w0), m_bits(w1), b0, b1);
+            for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[0][i], m_bits(w0), m_bits(w1), bq);
+        } else {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) c_mma_z(acc[j][i], a[0][i], m_bits(w0), m_bits(w1));
+        }
     }
 #pragma unroll
     for (int ks = 1; ks < KS; ++ks) {
@@ -121,11 +153,17 @@ HINT_DEV void c_layer_bd(const uint32_t (&a)[NT][MT][4], const float* __restrict
     const int t = lane & 3;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-        float b0 = 0.f, b1 = 0.f, w0, w1;
-        if (bl != nullptr) c_ldw2<WS>(bl + 8 * j + 2 * t, b0, b1);
+        float w0, w1;
         c_ldw2<WS>(Wl + j * 64 + 2 * lane, w0, w1);
+        if (bl != nullptr) {
+            float bq[4];
+            c_ldb4<WS>(bl + 16 * j + 4 * t, bq);
 #pragma unroll
-        for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[j][i], m_bits(w0), m_bits(w1), b0, b1);
+            for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[j][i], m_bits(w0), m_bits(w1), bq);
+        } else {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) c_mma_z(acc[j][i], a[j][i], m_bits(w0), m_bits(w1));
+        }
     }
 }
 template <bool WS, int MT, int NT, int BD>
@@ -372,7 +410,19 @@ hint_fwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
 //     TM samples of the tile, output tiles dealt round-robin to the warps, flushed to the CTA's private partial-gradient
 //     buffer (store on the first tile, red.global.add afterwards; reduced in fixed order by hint_reduce_unpack_kernel);
 //   barrier.
-HINT_DEV int c_swz(int col) { return (((col >> 1) & 3) << 1) ^ ((col & 1) << 2); }
+HINT_DEV int c_swz(int col) { return col & 7; }
+
+// ldmatrix of four 8x4 tf32 matrices (= 8x8 b16): lane l supplies the address of row l%8 (16 bytes) of matrix l/8 and
+// receives element (row l/4, column l%4) of every matrix - exactly the m16n8k8 A fragment (matrices: rows 0-7 / 8-15 x
+// k-slots 0-3 / 4-7) or two B fragments, in consecutive registers
+HINT_DEV void c_ldsm4(const float* rowp, uint32_t (&r)[4]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(rowp)));
+#elif !defined(__CUDACC__)
+    emu::ldsm4(rowp, r);
+#endif
+}
 
 // float index of the lane's R = 2*MT rows (samples 16*MT*warp + R*g ..) of column `col`
 template <int MT, int NW>
@@ -386,7 +436,7 @@ template <int TM>
 HINT_DEV int c_elem(int col, int m) { return col * TM + ((((m >> 2) ^ c_swz(col))) << 2) + (m & 3); }
 
 struct ChainBwdSmem {      // float offsets of the CTA's shared-memory regions
-    int xt, dz, hb1, hb2, gb1, gb2, go, dj, nodes, total;
+    int xt, dz, hb1, hb2, gb1, gb2, go, dj, cst, nodes, total;
 };
 template <int MT, int NW>
 HINT_HD constexpr ChainBwdSmem chain_bwd_smem(int d, int dc, int max_nh, int max_no, int n_nodes) {
@@ -401,7 +451,8 @@ HINT_HD constexpr ChainBwdSmem chain_bwd_smem(int d, int dc, int max_nh, int max
     s.gb2 = s.gb1 + 8 * max_nh * TM;
     s.go = s.gb2 + 8 * max_nh * TM;
     s.dj = s.go + 8 * max_no * TM;
-    s.nodes = s.dj + TM;
+    s.cst = s.dj + TM;          // 4 x 1.0f, 4 x 0.0f: the bias row / padding rows of the weight-gradient operands
+    s.nodes = s.cst + 8;
     s.total = s.nodes + 32 * n_nodes;
     return s;
 }
@@ -459,109 +510,153 @@ HINT_DEV void c_mask_to_a(const float (&acc)[NT][MT][4], const float* hbuf, cons
         }
 }
 
-// weight-gradient GEMM of one layer: CT[in-feature rows | ones row][out cols] += sum over the tile's samples.
-//   XIN: the in-features are the node's subnet inputs (x_upper' / condition columns of the x tile), else columns of `abuf`.
+// weight-gradient GEMM of one layer: CT[in-feature rows | ones row][out cols] += sum over the tile's samples.  Both operands
+// are fetched with ldmatrix from the swizzled [column][sample] buffers (a matrix row = 4 consecutive samples of one column).
+//   XIN: the in-features are the node's subnet inputs (tile columns in_col[] of the x tile, exact fp32: the tensor core
+//   truncates them), else columns of the buffer at `aoff`.
 //   rot: rotates the unit -> warp assignment so that the small GEMMs of one phase land on different warps
 template <int MT, int NW, int KSIN, int NTOUT, bool XIN>
-HINT_DEV void c_dw_gemm(const float* abuf, const short* in_col, const float* bbuf, float* __restrict__ part, bool first,
-                        int warp, int lane, int rot) {
+HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff, int cst, float* __restrict__ part, bool first,
+                        int warp, int lane, int rot, int exp) {
+    if (exp & 2) return;
     constexpr int TM = 16 * MT * NW;
     constexpr int MTC = (8 * KSIN + 1 + 15) / 16;
     constexpr int NC = NTOUT <= 5 ? NTOUT : 3;
     constexpr int NCH = NTOUT / NC;
+    constexpr int NP = (NC + 1) / 2;
     static_assert(NCH * NC == NTOUT, "n-chunking must tile the layer");
-    const int g = lane >> 2, t = lane & 3;
     for (int u = (warp + NW - rot) % NW; u < MTC * NCH; u += NW) {
         const int i = u / NCH, ch = u - i * NCH;
-        // A rows r0 = 16i + g, r1 = r0 + 8: feature column, the ones row (bias) or zero padding
-        int abase[2], amode[2];      // amode 0 load, 1 ones, 2 zero
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int r = 16 * i + 8 * hh + g;
-            int col = 0;
-            amode[hh] = 0;
-            if (XIN) {
-                if (r < 8 * KSIN) { col = in_col[r]; if (col < 0) { col = 0; amode[hh] = 2; } }
-                else amode[hh] = (r == 8 * KSIN) ? 1 : 2;
+        // A: matrix m = lane/8 -> rows 8*(m&1).. of the m-tile, chunk (m>>1) of the k-step
+        int abase, amask = ~0;
+        {
+            const int r = 16 * i + 8 * ((lane >> 3) & 1) + (lane & 7), hi = lane >> 4;
+            int col = -1;
+            if (r < 8 * KSIN) col = XIN ? (int)in_col[r] : r;
+            if (col >= 0) {
+                const int sw = c_swz(col);
+                abase = (XIN ? 0 : aoff) + col * TM + ((hi ^ (sw & 1)) << 2) + ((sw >> 1) << 3);
             } else {
-                if (r < 8 * KSIN) col = r;
-                else amode[hh] = (r == 8 * KSIN) ? 1 : 2;
+                abase = cst + (r == 8 * KSIN ? 0 : 4);
+                amask = 0;
             }
-            const int sw = c_swz(col);
-            abase[hh] = col * TM + (((t ^ sw) & 3) << 2) + ((sw >> 2) << 4);
         }
-        int bbase[NC];
+        // B: pair p = n-tiles (2p, 2p+1) of the chunk; matrix m -> n-tile 2p + (m>>1), chunk (m&1)
+        int bbase[NP], bmask[NP];
 #pragma unroll
-        for (int jj = 0; jj < NC; ++jj) {
-            const int col = 8 * (ch * NC + jj) + g;
-            const int sw = c_swz(col);
-            bbase[jj] = col * TM + (((t ^ sw) & 3) << 2) + ((sw >> 2) << 4);
+        for (int p = 0; p < NP; ++p) {
+            const int jj = 2 * p + (lane >> 4), hi = (lane >> 3) & 1;
+            if (jj < NC) {
+                const int col = 8 * (ch * NC + jj) + (lane & 7);
+                const int sw = c_swz(col);
+                bbase[p] = boff + col * TM + ((hi ^ (sw & 1)) << 2) + ((sw >> 1) << 3);
+                bmask[p] = ~0;
+            } else {
+                bbase[p] = cst + 4;
+                bmask[p] = 0;
+            }
         }
         float acc[NC][4];
 #pragma unroll
-        for (int jj = 0; jj < NC; ++jj)
+        for (int ks = 0; ks < TM / 8; ++ks) {
+            uint32_t a[4];
+            c_ldsm4(S + (abase ^ ((ks << 3) & amask)), a);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[jj][e] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < TM / 16; ++kk) {
-            float av[2][4];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                if (amode[hh] == 0) {
-                    const float* p = abuf + (abase[hh] ^ (kk << 4));
-#if defined(__CUDA_ARCH__)
-                    const float4 q = *reinterpret_cast<const float4*>(p);
-                    av[hh][0] = q.x; av[hh][1] = q.y; av[hh][2] = q.z; av[hh][3] = q.w;
-#else
-                    for (int e = 0; e < 4; ++e) av[hh][e] = p[e];
-#endif
+            for (int p = 0; p < NP; ++p) {
+                uint32_t b[4];
+                c_ldsm4(S + (bbase[p] ^ ((ks << 3) & bmask[p])), b);
+                if (ks == 0) {
+                    c_mma_z(acc[2 * p], a, b[0], b[1]);
+                    if (2 * p + 1 < NC) c_mma_z(acc[2 * p + 1], a, b[2], b[3]);
                 } else {
-                    const float v = amode[hh] == 1 ? 1.f : 0.f;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) av[hh][e] = v;
+                    m_mma(acc[2 * p], a, b[0], b[1]);
+                    if (2 * p + 1 < NC) m_mma(acc[2 * p + 1], a, b[2], b[3]);
                 }
-            }
-            uint32_t a0[4] = {m_bits(av[0][0]), m_bits(av[1][0]), m_bits(av[0][1]), m_bits(av[1][1])};
-            uint32_t a1[4] = {m_bits(av[0][2]), m_bits(av[1][2]), m_bits(av[0][3]), m_bits(av[1][3])};
-            if (XIN) {   // x columns are exact fp32: round them like every other operand
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { a0[e] += 0x1000u; a1[e] += 0x1000u; }
-            }
-#pragma unroll
-            for (int jj = 0; jj < NC; ++jj) {
-                const float* p = bbuf + (bbase[jj] ^ (kk << 4));
-                float bv[4];
-#if defined(__CUDA_ARCH__)
-                const float4 q = *reinterpret_cast<const float4*>(p);
-                bv[0] = q.x; bv[1] = q.y; bv[2] = q.z; bv[3] = q.w;
-#else
-                for (int e = 0; e < 4; ++e) bv[e] = p[e];
-#endif
-                m_mma(acc[jj], a0, m_bits(bv[0]), m_bits(bv[1]));
-                m_mma(acc[jj], a1, m_bits(bv[2]), m_bits(bv[3]));
             }
         }
         // flush: C fragment (i, j) = 128 floats, the lane's 4 are contiguous
-        {
+        if (exp & 1) continue;
 #pragma unroll
-            for (int jj = 0; jj < NC; ++jj) {
-                float* q = part + ((i * NTOUT + ch * NC + jj) * 32 + lane) * 4;
+        for (int jj = 0; jj < NC; ++jj) {
+            float* q = part + ((i * NTOUT + ch * NC + jj) * 32 + lane) * 4;
 #if defined(__CUDA_ARCH__)
-                if (first) *reinterpret_cast<float4*>(q) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
-                else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]) : "memory");
+            if (first) *reinterpret_cast<float4*>(q) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+            else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]) : "memory");
 #else
-                for (int e = 0; e < 4; ++e) { if (first) q[e] = acc[jj][e]; else q[e] += acc[jj][e]; }
+            for (int e = 0; e < 4; ++e) { if (first) q[e] = acc[jj][e]; else q[e] += acc[jj][e]; }
 #endif
-            }
         }
     }
 }
 
-// one (super) node of the backward sweep
+// s / t subnet keeping h1 / h2 (tf32) in the CTA-wide buffers at hb1 / hb2; L3 = also produce the output
+template <int MT, int TM, int KS1, int NH, int NO, int BD, bool L3>
+HINT_DEV void c_subnet_keep(const uint32_t (&a1)[KS1][MT][4], const float* __restrict__ Wnet, int lane, float* hb1, float* hb2,
+                            const int (&rp)[2], float (&out)[NO][MT][4]) {
+    using O = ChainOff<KS1, NH, NO, BD>;
+    uint32_t h[NH][MT][4];
+    {
+        float acc[NH][MT][4];
+        c_layer<false, MT, KS1, NH>(a1, Wnet + O::w1, Wnet + O::b1, lane, acc);
+        c_relu_to_a<MT, NH>(acc, h);
+    }
+    c_store_afrag<MT, TM, NH>(hb1, rp, h);
+    {
+        float acc[NH][MT][4];
+        c_layer_hh<false, MT, NH, BD>(h, Wnet + O::w2, Wnet + O::b2, lane, acc);
+        c_relu_to_a<MT, NH>(acc, h);
+    }
+    c_store_afrag<MT, TM, NH>(hb2, rp, h);
+    if (L3) c_layer<false, MT, NH, NO>(h, Wnet + O::w3, Wnet + O::b3, lane, out);
+}
+
+// dgrad chain of one net: dh2 = (dout W3)[h2>0] -> gb2, dh1 = (dh2 W2)[h1>0] -> gb1, dx_upper / dc += dh1 W1
+template <int MT, int NW, int KS1, int NH, int NO, int BD>
+HINT_DEV void c_dgrad(const uint32_t (&dout)[NO][MT][4], const float* __restrict__ Wb, const short* in_col, float* DZ, const float* hb1,
+                      const float* hb2, float* gb1, float* gb2, const int (&rp)[2], int warp, int lane) {
+    constexpr int TM = 16 * MT * NW, R = 2 * MT;
+    using O = ChainOff<KS1, NH, NO, BD>;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t gh[NH][MT][4];
+    {
+        float acc[NH][MT][4];
+        c_layer<false, MT, NO, NH>(dout, Wb + O::w3t, nullptr, lane, acc);
+        c_mask_to_a<MT, TM, NH>(acc, hb2, rp, gh);
+    }
+    c_store_afrag<MT, TM, NH>(gb2, rp, gh);
+    {
+        float acc[NH][MT][4];
+        c_layer_hh<false, MT, NH, BD>(gh, Wb + O::w2t, nullptr, lane, acc);
+        c_mask_to_a<MT, TM, NH>(acc, hb1, rp, gh);
+    }
+    c_store_afrag<MT, TM, NH>(gb1, rp, gh);
+    float da[KS1][MT][4];
+    c_layer<false, MT, NH, KS1>(gh, Wb + O::w1t, nullptr, lane, da);
+#pragma unroll
+    for (int j = 0; j < KS1; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = in_col[8 * j + 2 * t + c];
+            if (col >= 0) {
+                float* p = DZ + c_rows<MT, NW>(col, warp, g);
+                float v[R];
+                c_ld_rows<MT>(p, v);
+#pragma unroll
+                for (int i = 0; i < MT; ++i) { v[2 * i] += da[j][i][c]; v[2 * i + 1] += da[j][i][2 + c]; }
+                c_st_rows<MT>(p, v);
+            }
+        }
+}
+
+// one (super) node of the backward sweep.  Nodes with NH <= 4 keep BOTH nets' activations in the buffers (net e at n-tile
+// slots [e*NH, (e+1)*NH)): one private phase, one barrier pair; wider nodes run the nets one after the other and recompute
+// the hidden activations of the t subnet.
 template <int MT, int NW, int KS1, int NH, int NO, int BD>
 HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restrict__ Wn, const float* __restrict__ Wt,
-                         float* S, const ChainBwdSmem& L, float* __restrict__ part, bool first, int warp, int lane) {
+                         float* S, const ChainBwdSmem& L, float* __restrict__ part, bool first, int warp, int lane, int exp) {
     constexpr int TM = 16 * MT * NW, R = 2 * MT;
+    constexpr bool BOTH = NH <= 4;
+    constexpr int HS = 8 * NH * TM, OS = 8 * NO * TM;      // floats between the two nets' slots
     using O = ChainOff<KS1, NH, NO, BD>;
     const int g = lane >> 2, t = lane & 3;
     float* XT = S + L.xt;
@@ -575,23 +670,9 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
     uint32_t ds[NO][MT][4], dt[NO][MT][4];      // ds, dt as A fragments
     {
         float s[NO][MT][4], tt[NO][MT][4];
-        c_subnet<false, MT, KS1, NH, NO, BD>(a1, Wn + O::net, lane, tt);
-        {   // s subnet, keeping h1 / h2 in the CTA-wide buffers
-            uint32_t h[NH][MT][4];
-            {
-                float acc[NH][MT][4];
-                c_layer<false, MT, KS1, NH>(a1, Wn + O::w1, Wn + O::b1, lane, acc);
-                c_relu_to_a<MT, NH>(acc, h);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
-            {
-                float acc[NH][MT][4];
-                c_layer_hh<false, MT, NH, BD>(h, Wn + O::w2, Wn + O::b2, lane, acc);
-                c_relu_to_a<MT, NH>(acc, h);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
-            c_layer<false, MT, NH, NO>(h, Wn + O::w3, Wn + O::b3, lane, s);
-        }
+        if (BOTH) c_subnet_keep<MT, TM, KS1, NH, NO, BD, true>(a1, Wn + O::net, lane, S + L.hb1 + HS, S + L.hb2 + HS, rp, tt);
+        else c_subnet<false, MT, KS1, NH, NO, BD>(a1, Wn + O::net, lane, tt);
+        c_subnet_keep<MT, TM, KS1, NH, NO, BD, true>(a1, Wn, lane, S + L.hb1, S + L.hb2, rp, s);
         // coupling backward on the C fragments
         float dj[R];
         c_ld_rows<MT>(S + L.dj + 16 * MT * warp + R * g, dj);
@@ -633,82 +714,59 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
                     }
             }
     }
+    constexpr int rot2 = (O::mth * (NO <= 5 ? 1 : NO / 3)) % NW;
+    constexpr int rot3 = (rot2 + O::mth * (NH <= 5 ? 1 : NH / 3)) % NW;
+    constexpr int rotn = (rot3 + O::mt1 * (NH <= 5 ? 1 : NH / 3)) % NW;
+    if (BOTH) {
+        c_store_afrag<MT, TM, NO>(S + L.go, rp, ds);
+        c_store_afrag<MT, TM, NO>(S + L.go + OS, rp, dt);
+        c_dgrad<MT, NW, KS1, NH, NO, BD>(ds, Wt, nd->in_col, DZ, S + L.hb1, S + L.hb2, S + L.gb1, S + L.gb2, rp, warp, lane);
+        c_dgrad<MT, NW, KS1, NH, NO, BD>(dt, Wt + O::tnet, nd->in_col, DZ, S + L.hb1 + HS, S + L.hb2 + HS, S + L.gb1 + HS, S + L.gb2 + HS,
+                                         rp, warp, lane);
+        m_cta_sync();
 #pragma unroll 1
-    for (int net = 0; net < 2; ++net) {
-        const float* Wf = Wn + net * O::net;
-        const float* Wb = Wt + net * O::tnet;
-        uint32_t dout[NO][MT][4];
-#pragma unroll
-        for (int j = 0; j < NO; ++j)
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dout[j][i][e] = net ? dt[j][i][e] : ds[j][i][e];
-        if (net == 1) {   // recompute h1, h2 of the t subnet into the buffers
-            uint32_t h[NH][MT][4];
-            {
-                float acc[NH][MT][4];
-                c_layer<false, MT, KS1, NH>(a1, Wf + O::w1, Wf + O::b1, lane, acc);
-                c_relu_to_a<MT, NH>(acc, h);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.hb1, rp, h);
-            {
-                float acc[NH][MT][4];
-                c_layer_hh<false, MT, NH, BD>(h, Wf + O::w2, Wf + O::b2, lane, acc);
-                c_relu_to_a<MT, NH>(acc, h);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.hb2, rp, h);
-        }
-        c_store_afrag<MT, TM, NO>(S + L.go, rp, dout);
-        {
-            uint32_t gh[NH][MT][4];
-            {
-                float acc[NH][MT][4];
-                c_layer<false, MT, NO, NH>(dout, Wb + O::w3t, nullptr, lane, acc);
-                c_mask_to_a<MT, TM, NH>(acc, S + L.hb2, rp, gh);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.gb2, rp, gh);
-            {
-                float acc[NH][MT][4];
-                c_layer_hh<false, MT, NH, BD>(gh, Wb + O::w2t, nullptr, lane, acc);
-                c_mask_to_a<MT, TM, NH>(acc, S + L.hb1, rp, gh);
-            }
-            c_store_afrag<MT, TM, NH>(S + L.gb1, rp, gh);
-            float da[KS1][MT][4];
-            c_layer<false, MT, NH, KS1>(gh, Wb + O::w1t, nullptr, lane, da);
-#pragma unroll
-            for (int j = 0; j < KS1; ++j)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int col = nd->in_col[8 * j + 2 * t + c];
-                    if (col >= 0) {
-                        float* p = DZ + c_rows<MT, NW>(col, warp, g);
-                        float v[R];
-                        c_ld_rows<MT>(p, v);
-#pragma unroll
-                        for (int i = 0; i < MT; ++i) { v[2 * i] += da[j][i][c]; v[2 * i + 1] += da[j][i][2 + c]; }
-                        c_st_rows<MT>(p, v);
-                    }
-                }
+        for (int net = 0; net < 2; ++net) {
+            float* pn = part + net * O::dnet;
+            const int ho = net * HS, oo = net * OS, r0 = net * rotn;
+            c_dw_gemm<MT, NW, NH, NO, false>(S, L.hb2 + ho, nullptr, L.go + oo, L.cst, pn + O::dw3, first, warp, lane, r0 % NW, exp);
+            c_dw_gemm<MT, NW, NH, NH, false>(S, L.hb1 + ho, nullptr, L.gb2 + ho, L.cst, pn + O::dw2, first, warp, lane, (r0 + rot2) % NW, exp);
+            c_dw_gemm<MT, NW, KS1, NH, true>(S, L.xt, nd->in_col, L.gb1 + ho, L.cst, pn + O::dw1, first, warp, lane, (r0 + rot3) % NW, exp);
         }
         m_cta_sync();
-        float* pn = part + net * O::dnet;
-        c_dw_gemm<MT, NW, NH, NO, false>(S + L.hb2, nullptr, S + L.go, pn + O::dw3, first, warp, lane, 0);
-        c_dw_gemm<MT, NW, NH, NH, false>(S + L.hb1, nullptr, S + L.gb2, pn + O::dw2, first, warp, lane, (O::mth * (NO <= 5 ? 1 : NO / 3)) % NW);
-        c_dw_gemm<MT, NW, KS1, NH, true>(XT, nd->in_col, S + L.gb1, pn + O::dw1, first, warp, lane,
-                                         (O::mth * (NO <= 5 ? 1 : NO / 3) + O::mth * (NH <= 5 ? 1 : NH / 3)) % NW);
-        m_cta_sync();
+    } else {
+#pragma unroll 1
+        for (int net = 0; net < 2; ++net) {
+            uint32_t dout[NO][MT][4];
+#pragma unroll
+            for (int j = 0; j < NO; ++j)
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dout[j][i][e] = net ? dt[j][i][e] : ds[j][i][e];
+            if (net == 1) {   // recompute h1, h2 of the t subnet into the buffers
+                float unused[NO][MT][4];
+                c_subnet_keep<MT, TM, KS1, NH, NO, BD, false>(a1, Wn + O::net, lane, S + L.hb1, S + L.hb2, rp, unused);
+            }
+            c_store_afrag<MT, TM, NO>(S + L.go, rp, dout);
+            c_dgrad<MT, NW, KS1, NH, NO, BD>(dout, Wt + net * O::tnet, nd->in_col, DZ, S + L.hb1, S + L.hb2, S + L.gb1, S + L.gb2, rp, warp, lane);
+            m_cta_sync();
+            float* pn = part + net * O::dnet;
+            c_dw_gemm<MT, NW, NH, NO, false>(S, L.hb2, nullptr, L.go, L.cst, pn + O::dw3, first, warp, lane, 0, exp);
+            c_dw_gemm<MT, NW, NH, NH, false>(S, L.hb1, nullptr, L.gb2, L.cst, pn + O::dw2, first, warp, lane, rot2, exp);
+            c_dw_gemm<MT, NW, KS1, NH, true>(S, L.xt, nd->in_col, L.gb1, L.cst, pn + O::dw1, first, warp, lane, rot3, exp);
+            m_cta_sync();
+        }
     }
 }
 
 template <int MT, int NW>
 HINT_DEV void c_node_bwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* S, const ChainBwdSmem& L,
-                                  float* __restrict__ partial, bool first, int warp, int lane) {
-    const float* Wn = W + nd->w_off;
-    const float* Wt = W + nd->wt_off;
+                                  float* __restrict__ partial, bool first, int warp, int lane, int exp) {
+    const float* Wn = W + ((exp & 4) ? 0 : nd->w_off);
+    const float* Wt = W + ((exp & 4) ? 0 : nd->wt_off);
     float* part = partial + nd->dw_off;
 #define HINT_CHAIN_CASE(ID, A, B, C, D) \
-    case ID: c_node_bwd<MT, NW, A, B, C, D>(nd, alpha, Wn, Wt, S, L, part, first, warp, lane); break;
+    case ID: c_node_bwd<MT, NW, A, B, C, D>(nd, alpha, Wn, Wt, S, L, part, first, warp, lane, exp); break;
     switch (nd->shape) {
         HINT_CHAIN_SHAPES(HINT_CHAIN_CASE)
         default: break;
@@ -779,6 +837,7 @@ HINT_DEV void c_bwd_body(const ChainTables& T, const ChainNode* nodes, const Cha
     float* partial = partials + (long long)bid * n_partial;
     const long long ntiles = (B + TM - 1) / TM;
     bool first = true;
+    if (tid < 8) S[L.cst + tid] = tid < 4 ? 1.f : 0.f;
     for (long long tile = bid; tile < ntiles; tile += nblocks) {
         const long long row0 = tile * TM;
         const int rows = (int)((B - row0) < TM ? (B - row0) : TM);
@@ -789,7 +848,7 @@ HINT_DEV void c_bwd_body(const ChainTables& T, const ChainNode* nodes, const Cha
         for (int i = tid; i < TM; i += NT) S[L.dj + i] = (i < rows) ? dlogdet[row0 + i] : 0.f;
         m_cta_sync();
         for (int q = T.n_nodes - 1; q >= 0; --q)
-            c_node_bwd_dispatch<MT, NW>(nodes + q, T.alpha, W, S, L, partial, first, warp, lane);
+            c_node_bwd_dispatch<MT, NW>(nodes + q, T.alpha, W, S, L, partial, first, warp, lane, T.exp);
         if (x_rec) c_store_tile_sw<TM, NT>(S + L.xt, 0, x_rec, row0, rows, T.d, tid);
         c_store_tile_sw<TM, NT>(S + L.dz, 0, dx, row0, rows, T.d, tid);
         if (dc) c_store_tile_sw<TM, NT>(S + L.dz, T.d, dc, row0, rows, T.dc, tid);

@@ -14,6 +14,11 @@ namespace {
 // forward / inverse configuration: MT = 1 (16 samples per warp) with as many warps as fit next to the shared-memory
 // resident operands (WS), else 16 warps reading the operands through L1.  HINT_B200_CHAIN_FWD=<mt><nw><ws> (e.g. "2080",
 // "1161") overrides (developer aid).
+int chain_exp() {
+    static const int v = [] { const char* e = std::getenv("HINT_B200_CHAIN_EXP"); return e ? std::atoi(e) : 0; }();
+    return v;
+}
+
 struct FwdCfg { int mt, nw, ws; size_t smem; };
 
 template <int MT, int NW, bool WS>
@@ -125,7 +130,7 @@ int chain_bwd_ctas(const ChainPlan& c, const DevChain& d, long long B) {
 cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& d, int grid, const float* z, const float* cond,
                              const float* packed, const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc,
                              float* partials, long long B, cudaStream_t st) {
-    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed};
+    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed, chain_exp()};
     const BwdCfg b{d.bwd_mt, d.bwd_nw};
     const ChainBwdSmem L = bwd_layout(p, c, b);
     const long long np = c.n_partial;
@@ -140,7 +145,7 @@ cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& 
 
 cudaError_t chain_launch_fwd(const Plan& p, const ChainPlan& c, const DevChain& d, const float* x, const float* cond,
                              const float* packed, float* z, float* logdet, long long B, int rev, cudaStream_t st) {
-    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed};
+    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed, chain_exp()};
     const FwdCfg f = pick_fwd(p, c);
     const int RW = 16 * f.mt;
     const long long ntiles = (B + RW - 1) / RW;

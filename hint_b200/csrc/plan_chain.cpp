@@ -98,8 +98,9 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
         w_off[q] = off; off += 2 * (int64_t)o.net;
         wt_off[q] = toff; toff += 2 * (int64_t)o.tnet;
         dw_off[q] = doff; doff += 2 * (int64_t)o.dnet;
-        c.max_nh = std::max(c.max_nh, cs.nh);
-        c.max_no = std::max(c.max_no, cs.no);
+        // buffer slots (n-tiles): nodes with nh <= 4 keep both nets' activations at once (chain_kernels.cuh: c_node_bwd)
+        c.max_nh = std::max(c.max_nh, cs.nh <= 4 ? 2 * cs.nh : cs.nh);
+        c.max_no = std::max(c.max_no, cs.nh <= 4 ? 2 * cs.no : cs.no);
     }
     c.n_fwd_packed = off;
     c.n_packed = off + toff;
@@ -140,7 +141,12 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                 const int64_t w3 = poff(p, i, net, 2, 0), b3 = poff(p, i, net, 2, 1);
                 auto set = [&](int64_t idx, int64_t src) { c.pack_src[(size_t)(base + idx)] = (int32_t)src; };
                 auto sett = [&](int64_t idx, int64_t src) { c.pack_src[(size_t)(tbase + idx)] = (int32_t)src; };
-                auto set_exact = [&](int64_t idx, int64_t src) { c.pack_src[(size_t)(base + idx)] = (int32_t)(-src - 2); };
+                // bias u of an operand at `reg`: quad positions (u%2) and (u%2)+2 of the 16-float record of n-tile u/8
+                auto set_bias = [&](int64_t reg, int u, int64_t src) {
+                    const int64_t q = reg + (u >> 3) * 16 + ((u & 7) >> 1) * 4 + (u & 1);
+                    c.pack_src[(size_t)(base + q)] = (int32_t)(-src - 2);
+                    c.pack_src[(size_t)(base + q + 2)] = (int32_t)(-src - 2);
+                };
                 auto un = [&](int64_t param, int64_t idx) { c.unpack_src[(size_t)param] = (int32_t)(dbase + idx); };
                 for (int u = 0; u < nd.h; ++u) {
                     for (int f = 0; f < nd.cin; ++f) {
@@ -149,7 +155,7 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                         sett(o.w1t + frag(KS1, hb + u, feat(f)), src);              // B[u][f] = W1[u][f]
                         un(src, o.dw1 + cfrag(NH, feat(f), hb + u));
                     }
-                    set_exact(o.b1 + hb + u, b1 + u);
+                    set_bias(o.b1, hb + u, b1 + u);
                     un(b1 + u, o.dw1 + cfrag(NH, 8 * KS1, hb + u));
                     for (int v = 0; v < nd.h; ++v) {
                         const int64_t src = w2 + (int64_t)u * nd.h + v;
@@ -162,7 +168,7 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                         }
                         un(src, o.dw2 + cfrag(NH, hb + v, hb + u));
                     }
-                    set_exact(o.b2 + hb + u, b2 + u);
+                    set_bias(o.b2, hb + u, b2 + u);
                     un(b2 + u, o.dw2 + cfrag(NH, 8 * NH, hb + u));
                 }
                 for (int r = 0; r < nd.cout; ++r) {
@@ -172,7 +178,7 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                         sett(o.w3t + frag(NH, co + r, hb + v), src);                // B[r][v] = W3[r][v]
                         un(src, o.dw3 + cfrag(NO, hb + v, co + r));
                     }
-                    set_exact(o.b3 + co + r, b3 + r);
+                    set_bias(o.b3, co + r, b3 + r);
                     un(b3 + r, o.dw3 + cfrag(NO, 8 * NH, co + r));
                 }
             }

@@ -41,11 +41,11 @@ int emul_chain_run(int d, int dc, const int* c_internal, int n_internal, double 
     if (!err.empty()) return code ? code : 1;
     ChainPlan cp;
     build_chain_plan(p, cp);
-    info[0] = cp.ok; info[1] = cp.n_packed; info[2] = cp.n_partial; info[3] = cp.n_nodes; info[4] = cp.max_nh;
+    info[0] = cp.ok; info[1] = cp.n_packed; info[2] = cp.n_partial; info[3] = cp.n_nodes; info[4] = cp.max_nh; info[6] = cp.n_fwd_packed;
     if (!cp.ok) return 50;
     std::vector<float> W((size_t)cp.n_packed + 4);
     for (int64_t i = 0; i < cp.n_packed; ++i) { float lo; m_pack_elem(cp.pack_src[(size_t)i], params, W[(size_t)i], lo); }
-    ChainTables T{cp.n_nodes, p.d, p.dc, p.alpha, (int)cp.n_fwd_packed};
+    ChainTables T{cp.n_nodes, p.d, p.dc, p.alpha, (int)cp.n_fwd_packed, 0};
     const int bwd_cfg = mt;
     mt = mt == 2 ? 2 : 1;     // forward configuration
     {

@@ -25,6 +25,7 @@ namespace hint { namespace emu {
 struct WarpX {
     int count = 0;
     unsigned gen = 0;
+    const float* rowp[32];
     uint32_t a[32][4];
     uint32_t b[32][2];
 };
@@ -65,6 +66,17 @@ static void warp_rendezvous(WarpX& w) {
 }
 
 void warp_sync() { warp_rendezvous(g_cta->warps[g_cta->cur >> 5]); }
+
+// ldmatrix.m8n8.x4 on 32-bit elements: lane l supplies row l%8 of matrix l/8; r[m] = element (row lane/4, column lane%4)
+void ldsm4(const float* rowp, uint32_t (&r)[4]) {
+    Cta* cta = g_cta;
+    const int lane = cta->cur & 31;
+    WarpX& w = cta->warps[cta->cur >> 5];
+    w.rowp[lane] = rowp;
+    warp_rendezvous(w);
+    for (int m = 0; m < 4; ++m) std::memcpy(&r[m], w.rowp[8 * m + (lane >> 2)] + (lane & 3), 4);
+    warp_rendezvous(w);
+}
 
 static inline float tf32(uint32_t u) {
     u &= 0xFFFFE000u;
