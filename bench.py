@@ -326,10 +326,17 @@ def run_ours(args, w, name):
         traffic = json.load(open(tpath)).get(name, {}).get("bwd_dram_bytes_per_launch")
     kname = {"fp32": "hint_bwd_fp32_kernel", "tf32_tcgen05": "hint_bwd_fp32_kernel", "tf32x3": "hint_bwd_mma_kernel<TM,3xTF32>"}.get(
         args.mode, "hint_bwd_mma_kernel<TM,TF32>")
+    chain = args.mode in ("tf32", "tf32_chain") and blk.plan.mode_supported("tf32_chain") and os.environ.get("HINT_B200_TF32_BWD") != "mma"
+    if chain:
+        kname = "hint_bwd_chain_kernel<MT=1,NW=4> (register-chained warp-MMA)"
+    # second denominator: what mma.sync.m16n8k8 tf32 itself sustains on this chip (profiles/ubench5_r01_mma_sync_tf32.txt);
+    # the kernels of this path issue warp-level MMAs, tcgen05 does not fit the 8..72-wide layers
+    mma_sync_peak = 270.0
     roofline = {"bound": "tensor", "kernel": f"{kname} (one block, B={B})", "achieved": achieved,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
                 "peak_source": f"TF32 dense = bf16_tflops_sustained/2 of {peak_src}",
                 "flops_per_launch": 2 * Fb * B, "ms_per_launch": ms_b,
+                "frac_of_mma_sync_tf32_peak": achieved / mma_sync_peak, "mma_sync_tf32_peak_tflops": mma_sync_peak,
                 "fwd_kernel": {"achieved": Fb * B / (ms_f * 1e-3) / 1e12, "ms_per_launch": ms_f},
                 "hbm_gbs_fwd_streaming": (2 * w["d"] + 1 + w["dc"]) * 4 * B / (ms_f * 1e-3) / 1e9,
                 "note": "launch = pack + fused kernel (+ partial-gradient reduce), timed with CUDA events on the launch stream"}

@@ -95,6 +95,10 @@ class TreePlan:
     def tile_rows(self, which=_lib.WS_FORWARD):
         return int(self._lib.hint_plan_tile_rows(self._h, which))
 
+    def mode_supported(self, mode: str) -> bool:
+        """True when this block fits the kernel family behind `mode` (every family has a shape / shared-memory envelope)."""
+        return bool(self._lib.hint_plan_mode_supported(self._h, _MODES[mode]))
+
     # -- launches ------------------------------------------------------------------------------
     @staticmethod
     def _check(t, name, shape=None):

@@ -345,20 +345,32 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
     float* XT = S + warp * chain_fwd_warp_floats<MT>(T.d, T.dc);
     float* JP = XT + (T.d + T.dc) * (RW + 4);
     const long long ntiles = (B + RW - 1) / RW;
-    for (long long tile = (long long)bid * NW + warp; tile < ntiles; tile += (long long)nblocks * NW) {
+    // The warps are independent, but they all run the same (large, fully unrolled) instruction stream: a CTA barrier per
+    // tile (T.exp & 8) or per node (T.exp & 16) keeps them in step so they share the instruction cache.
+    for (long long base = (long long)bid * NW; base < ntiles; base += (long long)nblocks * NW) {
+        const long long tile = base + warp;
+        const bool live = tile < ntiles;
         const long long row0 = tile * RW;
-        const int rows = (int)((B - row0) < RW ? (B - row0) : RW);
-        c_load_tile<MT>(XT, 0, x, row0, rows, T.d, lane);
-        c_load_tile<MT>(XT, T.d, c, row0, rows, T.dc, lane);
-        for (int i = lane; i < 4 * RW; i += 32) JP[i] = 0.f;
-        c_syncwarp();
-        for (int q = 0; q < T.n_nodes; ++q) {
-            c_node_fwd_dispatch<WS, MT, REV>(nodes + (REV ? T.n_nodes - 1 - q : q), T.alpha, W, XT, JP, lane);
+        const int rows = !live ? 0 : (int)((B - row0) < RW ? (B - row0) : RW);
+        if (live) {
+            c_load_tile<MT>(XT, 0, x, row0, rows, T.d, lane);
+            c_load_tile<MT>(XT, T.d, c, row0, rows, T.dc, lane);
+            for (int i = lane; i < 4 * RW; i += 32) JP[i] = 0.f;
             c_syncwarp();
         }
-        c_store_tile<MT>(XT, 0, z, row0, rows, T.d, lane);
-        if (lane < rows) logdet[row0 + lane] = JP[lane] + JP[RW + lane] + JP[2 * RW + lane] + JP[3 * RW + lane];
-        c_syncwarp();
+        for (int q = 0; q < T.n_nodes; ++q) {
+            if (live) {
+                c_node_fwd_dispatch<WS, MT, REV>(nodes + (REV ? T.n_nodes - 1 - q : q), T.alpha, W, XT, JP, lane);
+                c_syncwarp();
+            }
+            if (T.exp & 16) m_cta_sync();
+        }
+        if (live) {
+            c_store_tile<MT>(XT, 0, z, row0, rows, T.d, lane);
+            if (lane < rows) logdet[row0 + lane] = JP[lane] + JP[RW + lane] + JP[2 * RW + lane] + JP[3 * RW + lane];
+            c_syncwarp();
+        }
+        if (T.exp & 8) m_cta_sync();
     }
 }
 
