@@ -283,6 +283,8 @@ HINT_DEV void c_load_tile(float* XT, int col_base, const float* __restrict__ gsr
     if (width == 0) return;
     const float* src = gsrc + row0 * width;
     const int nvalid = rows * width, n = RW * width;
+    int m0 = (lane * 4) / width, j0 = lane * 4 - m0 * width;      // (row, column) of element i, advanced without divisions
+    const int dm = 128 / width, dj = 128 - dm * width;
     for (int i = lane * 4; i < n; i += 128) {
         float v[4];
         if (i + 3 < nvalid) {
@@ -296,12 +298,14 @@ HINT_DEV void c_load_tile(float* XT, int col_base, const float* __restrict__ gsr
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = (i + e < nvalid) ? src[i + e] : 0.f;
         }
-        int m = i / width, j = i - m * width;
+        int m = m0, j = j0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             XT[(col_base + j) * PW + m] = v[e];
             if (++j == width) { j = 0; ++m; }
         }
+        m0 += dm; j0 += dj;
+        if (j0 >= width) { j0 -= width; ++m0; }
     }
 }
 template <int MT>
@@ -310,14 +314,18 @@ HINT_DEV void c_store_tile(const float* XT, int col_base, float* __restrict__ gd
     if (width == 0) return;
     float* dst = gdst + row0 * width;
     const int nvalid = rows * width;
+    int m0 = (lane * 4) / width, j0 = lane * 4 - m0 * width;
+    const int dm = 128 / width, dj = 128 - dm * width;
     for (int i = lane * 4; i < nvalid; i += 128) {
         float v[4];
-        int m = i / width, j = i - m * width;
+        int m = m0, j = j0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             v[e] = XT[(col_base + j) * PW + m];
             if (++j == width) { j = 0; ++m; }
         }
+        m0 += dm; j0 += dj;
+        if (j0 >= width) { j0 -= width; ++m0; }
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
             *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
@@ -423,6 +431,19 @@ hint_fwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
 //     buffer (store on the first tile, red.global.add afterwards; reduced in fixed order by hint_reduce_unpack_kernel);
 //   barrier.
 HINT_DEV int c_swz(int col) { return col & 7; }
+
+// developer aid (T.exp & 32): thread 0 of CTA 0 records clock64 at the phase boundaries of the backward sweep
+#if defined(__CUDACC__)
+__device__ long long g_chain_dbg[2048];
+#endif
+HINT_DEV void c_stamp(int exp, int warp, int lane) {
+#if defined(__CUDA_ARCH__)
+    if ((exp & 32) && warp == 0 && lane == 0 && blockIdx.x == 0) {
+        const long long n = g_chain_dbg[0];
+        if (n < 2040) { g_chain_dbg[1 + n] = clock64(); g_chain_dbg[0] = n + 1; }
+    }
+#endif
+}
 
 // ldmatrix of four 8x4 tf32 matrices (= 8x8 b16): lane l supplies the address of row l%8 (16 bytes) of matrix l/8 and
 // receives element (row l/4, column l%4) of every matrix - exactly the m16n8k8 A fragment (matrices: rows 0-7 / 8-15 x
@@ -568,21 +589,29 @@ HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff,
                 bmask[p] = 0;
             }
         }
+        // operands of k-step ks+1 are fetched before the MMAs of k-step ks are issued (the asm statements keep program order,
+        // so this IS the schedule): the ldmatrix latency overlaps the tensor pipe
         float acc[NC][4];
+        uint32_t a[2][4], b[2][NP][4];
+        c_ldsm4(S + abase, a[0]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) c_ldsm4(S + bbase[p], b[0][p]);
 #pragma unroll
         for (int ks = 0; ks < TM / 8; ++ks) {
-            uint32_t a[4];
-            c_ldsm4(S + (abase ^ ((ks << 3) & amask)), a);
+            const int cur = ks & 1, nxt = cur ^ 1;
+            if (ks + 1 < TM / 8) {
+                c_ldsm4(S + (abase ^ (((ks + 1) << 3) & amask)), a[nxt]);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) c_ldsm4(S + (bbase[p] ^ (((ks + 1) << 3) & bmask[p])), b[nxt][p]);
+            }
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                uint32_t b[4];
-                c_ldsm4(S + (bbase[p] ^ ((ks << 3) & bmask[p])), b);
                 if (ks == 0) {
-                    c_mma_z(acc[2 * p], a, b[0], b[1]);
-                    if (2 * p + 1 < NC) c_mma_z(acc[2 * p + 1], a, b[2], b[3]);
+                    c_mma_z(acc[2 * p], a[cur], b[cur][p][0], b[cur][p][1]);
+                    if (2 * p + 1 < NC) c_mma_z(acc[2 * p + 1], a[cur], b[cur][p][2], b[cur][p][3]);
                 } else {
-                    m_mma(acc[2 * p], a, b[0], b[1]);
-                    if (2 * p + 1 < NC) m_mma(acc[2 * p + 1], a, b[2], b[3]);
+                    m_mma(acc[2 * p], a[cur], b[cur][p][0], b[cur][p][1]);
+                    if (2 * p + 1 < NC) m_mma(acc[2 * p + 1], a[cur], b[cur][p][2], b[cur][p][3]);
                 }
             }
         }
@@ -677,6 +706,7 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
     int rp[2];
     rp[0] = c_rows<MT, NW>(2 * t, warp, g);
     rp[1] = c_rows<MT, NW>(2 * t + 1, warp, g);
+    c_stamp(exp, warp, lane);
     uint32_t a1[KS1][MT][4];
     c_load_input_sw<MT, NW, KS1>(XT, nd->in_col, warp, lane, a1);
     uint32_t ds[NO][MT][4], dt[NO][MT][4];      // ds, dt as A fragments
@@ -735,7 +765,9 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
         c_dgrad<MT, NW, KS1, NH, NO, BD>(ds, Wt, nd->in_col, DZ, S + L.hb1, S + L.hb2, S + L.gb1, S + L.gb2, rp, warp, lane);
         c_dgrad<MT, NW, KS1, NH, NO, BD>(dt, Wt + O::tnet, nd->in_col, DZ, S + L.hb1 + HS, S + L.hb2 + HS, S + L.gb1 + HS, S + L.gb2 + HS,
                                          rp, warp, lane);
+        c_stamp(exp, warp, lane);
         m_cta_sync();
+        c_stamp(exp, warp, lane);
 #pragma unroll 1
         for (int net = 0; net < 2; ++net) {
             float* pn = part + net * O::dnet;
@@ -744,6 +776,7 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
             c_dw_gemm<MT, NW, NH, NH, false>(S, L.hb1 + ho, nullptr, L.gb2 + ho, L.cst, pn + O::dw2, first, warp, lane, (r0 + rot2) % NW, exp);
             c_dw_gemm<MT, NW, KS1, NH, true>(S, L.xt, nd->in_col, L.gb1 + ho, L.cst, pn + O::dw1, first, warp, lane, (r0 + rot3) % NW, exp);
         }
+        c_stamp(exp, warp, lane);
         m_cta_sync();
     } else {
 #pragma unroll 1
@@ -761,11 +794,14 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
             }
             c_store_afrag<MT, TM, NO>(S + L.go, rp, dout);
             c_dgrad<MT, NW, KS1, NH, NO, BD>(dout, Wt + net * O::tnet, nd->in_col, DZ, S + L.hb1, S + L.hb2, S + L.gb1, S + L.gb2, rp, warp, lane);
+            c_stamp(exp, warp, lane);
             m_cta_sync();
+            c_stamp(exp, warp, lane);
             float* pn = part + net * O::dnet;
             c_dw_gemm<MT, NW, NH, NO, false>(S, L.hb2, nullptr, L.go, L.cst, pn + O::dw3, first, warp, lane, 0, exp);
             c_dw_gemm<MT, NW, NH, NH, false>(S, L.hb1, nullptr, L.gb2, L.cst, pn + O::dw2, first, warp, lane, rot2, exp);
             c_dw_gemm<MT, NW, KS1, NH, true>(S, L.xt, nd->in_col, L.gb1, L.cst, pn + O::dw1, first, warp, lane, rot3, exp);
+            c_stamp(exp, warp, lane);
             m_cta_sync();
         }
     }
@@ -792,6 +828,9 @@ HINT_DEV void c_load_tile_sw(float* buf, int col_base, const float* __restrict__
     if (width == 0) return;
     const float* src = gsrc + row0 * width;
     const int nvalid = rows * width, n = TM * width;
+    // (row, column) of element i without a division per iteration: one divmod up front, then constant strides
+    int m0 = (tid * 4) / width, j0 = tid * 4 - m0 * width;
+    const int dm = (NT * 4) / width, dj = NT * 4 - dm * width;
     for (int i = tid * 4; i < n; i += NT * 4) {
         float v[4];
         if (i + 3 < nvalid) {
@@ -804,12 +843,14 @@ HINT_DEV void c_load_tile_sw(float* buf, int col_base, const float* __restrict__
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = (i + e < nvalid) ? src[i + e] : 0.f;
         }
-        int m = i / width, j = i - m * width;
+        int m = m0, j = j0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             buf[c_elem<TM>(col_base + j, m)] = v[e];
             if (++j == width) { j = 0; ++m; }
         }
+        m0 += dm; j0 += dj;
+        if (j0 >= width) { j0 -= width; ++m0; }
     }
 }
 template <int TM, int NT>
@@ -817,14 +858,18 @@ HINT_DEV void c_store_tile_sw(const float* buf, int col_base, float* __restrict_
     if (width == 0) return;
     float* dst = gdst + row0 * width;
     const int nvalid = rows * width;
+    int m0 = (tid * 4) / width, j0 = tid * 4 - m0 * width;
+    const int dm = (NT * 4) / width, dj = NT * 4 - dm * width;
     for (int i = tid * 4; i < nvalid; i += NT * 4) {
         float v[4];
-        int m = i / width, j = i - m * width;
+        int m = m0, j = j0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             v[e] = buf[c_elem<TM>(col_base + j, m)];
             if (++j == width) { j = 0; ++m; }
         }
+        m0 += dm; j0 += dj;
+        if (j0 >= width) { j0 -= width; ++m0; }
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
             *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);

@@ -2,7 +2,9 @@
 #include "chain_launch.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "chain_kernels.cuh"
@@ -140,6 +142,16 @@ cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& 
         hint_bwd_chain_kernel<1, 8, 1><<<grid, 256, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
     else
         hint_bwd_chain_kernel<2, 4, 1><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
+    if (T.exp & 32) {   // developer aid: phase-boundary cycle stamps of CTA 0 (HINT_B200_CHAIN_EXP=32)
+        static long long h[2048];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_chain_dbg, sizeof(h));
+        std::fprintf(stderr, "[hint_b200 chain dbg] %lld stamps; deltas:", h[0]);
+        for (long long i = 1; i < h[0]; ++i) std::fprintf(stderr, " %lld", h[1 + i] - h[i]);
+        std::fprintf(stderr, "\n");
+        std::memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_chain_dbg, h, sizeof(h));
+    }
     return cudaGetLastError();
 }
 
