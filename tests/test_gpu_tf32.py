@@ -165,3 +165,41 @@ def test_backward_tensor_core_modes(cfg, mode, tol):
     assert _l2(xrec, x.double().numpy()) < (5e-3 if mode == "tf32" else 1e-5)
     if dc:   # dc sums the input gradients of EVERY node's subnets (hint.py:76), so it collects the most TF32 rounding noise
         assert _l2(dcc, dc_ref.numpy()) < 1.5 * tol
+
+
+def test_full_size_properties_chain():
+    """BASELINE.json sizes (d=43 `hint_8` widths, batch 256k) through the register-chained kernels: size-independent
+    properties instead of the CPU oracle - f^-1(f(x)) = x and J_rev(f(x)) = -J_fwd(x) within the TF32 bound, agreement with
+    the FP32 CUDA-core kernels on the same inputs, bit-reproducibility, and exact linearity of the gradients in the upstream
+    gradient (scaling by 2 commutes with tf32 rounding)."""
+    dev = torch.device("cuda:0")
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    torch.manual_seed(11)
+    B, d = 262144, 43
+    blk = HierarchicalAffineCouplingBlock([(d,)], c_internal=[67, 33, 16, 8]).to(dev)
+    assert blk.plan.mode_supported("tf32_chain")
+    flat = blk.flat.detach()
+    x = torch.randn(B, d, device=dev)
+    with torch.no_grad():
+        z, J = blk.plan.forward(x, None, flat, mode="tf32_chain")
+        z2, J2 = blk.plan.forward(x, None, flat, mode="tf32_chain")
+        assert torch.equal(z, z2) and torch.equal(J, J2)
+        z32, J32 = blk.plan.forward(x, None, flat, mode="fp32")
+        scale = max(1.0, z32.abs().max().item())
+        assert (z - z32).abs().max().item() < TF32_TOL * scale
+        assert (J - J32).abs().max().item() < TF32_TOL * max(1.0, J32.abs().max().item())
+        xr, Jr = blk.plan.forward(z, None, flat, rev=True, mode="tf32_chain")
+        assert (xr - x).abs().max().item() < TF32_TOL * scale
+        assert (J + Jr).abs().max().item() < TF32_TOL * max(1.0, J32.abs().max().item())
+        dz = torch.randn(B, d, device=dev) / B
+        dJ = torch.randn(B, device=dev) / B
+        dx1, _, g1, xrec = blk.plan.backward(z, None, flat, dz, dJ, mode="tf32_chain", want_xrec=True)
+        dx2, _, g2, _ = blk.plan.backward(z, None, flat, 2 * dz, 2 * dJ, mode="tf32_chain")
+        dx3, _, g3, _ = blk.plan.backward(z, None, flat, dz, dJ, mode="tf32_chain")
+        dxf, _, gf, _ = blk.plan.backward(z, None, flat, dz, dJ, mode="fp32")
+    assert (xrec - x).abs().max().item() < TF32_TOL * scale
+    assert torch.equal(g1, g3) and torch.equal(dx1, dx3)           # per-CTA partial buffers, fixed-order reduction
+    assert (g2 - 2 * g1).abs().max().item() <= 1e-5 * g1.abs().max().item() + 1e-7
+    assert (dx2 - 2 * dx1).abs().max().item() <= 1e-5 * dx1.abs().max().item() + 1e-9
+    rel = lambda a, b: (torch.linalg.norm(a.double() - b.double()) / torch.linalg.norm(b.double())).item()
+    assert rel(g1, gf) < 2e-2 and rel(dx1, dxf) < 2e-2
