@@ -13,7 +13,7 @@
 #include "plan_chain.h"
 
 #if !defined(__CUDACC__)
-namespace hint { namespace emu { void warp_sync(); void ldsm4(const float* rowp, uint32_t (&r)[4]); } }
+namespace hint { namespace emu { void warp_sync(); void ldsm4(const float* rowp, uint32_t (&r)[4]); float shfl_xor(float v, int mask); } }
 #endif
 
 namespace hint {
@@ -25,6 +25,16 @@ struct ChainTables {
     int exp;            // developer experiments (timing only, WRONG results): 1 no partial flush, 2 no dW GEMMs, 4 all operand
                         // loads hit the first 4 KB of the packed buffer (HINT_B200_CHAIN_EXP)
 };
+
+HINT_DEV float c_shfl_xor(float v, int mask) {
+#if defined(__CUDA_ARCH__)
+    return __shfl_xor_sync(0xffffffffu, v, mask);
+#elif !defined(__CUDACC__)
+    return emu::shfl_xor(v, mask);
+#else
+    return v;
+#endif
+}
 
 HINT_DEV void c_syncwarp() {
 #if defined(__CUDA_ARCH__)
@@ -126,7 +136,8 @@ HINT_DEV void c_layer(const uint32_t (&a)[KS][MT][4], const float* __restrict__ 
         c_ldw2<WS>(Wl + j * 64 + 2 * lane, w0, w1);
         if (bl != nullptr) {
             float bq[4];
-            c_ldb4<WS>(bl + 16 * j + 4 * t, bq);
+            c_ldw2<WS>(bl + 8 * j + 2 * t, bq[0], bq[1]);
+            bq[2] = bq[0]; bq[3] = bq[1];
 #pragma unroll
             for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[0][i], m_bits(w0), m_bits(w1), bq);
         } else {
@@ -157,7 +168,8 @@ HINT_DEV void c_layer_bd(const uint32_t (&a)[NT][MT][4], const float* __restrict
         c_ldw2<WS>(Wl + j * 64 + 2 * lane, w0, w1);
         if (bl != nullptr) {
             float bq[4];
-            c_ldb4<WS>(bl + 16 * j + 4 * t, bq);
+            c_ldw2<WS>(bl + 8 * j + 2 * t, bq[0], bq[1]);
+            bq[2] = bq[0]; bq[3] = bq[1];
 #pragma unroll
             for (int i = 0; i < MT; ++i) c_mma_c(acc[j][i], a[j][i], m_bits(w0), m_bits(w1), bq);
         } else {
@@ -225,7 +237,7 @@ HINT_DEV void c_subnet(const uint32_t (&a1)[KS1][MT][4], const float* __restrict
 
 // one (super) node, forward (hint.py:79-81) or inverse (hint.py:82-84) coupling; JP = the lane's private log-det partials
 template <bool WS, int MT, int KS1, int NH, int NO, int BD, bool REV>
-HINT_DEV void c_node_fwd(const ChainNode* nd, float alpha, const float* __restrict__ Wn, float* XT, float* JP, int lane) {
+HINT_DEV void c_node_fwd(const ChainNode* nd, float alpha, const float* __restrict__ Wn, float* XT, float (&jl)[2 * MT], int lane) {
     constexpr int PW = 16 * MT + 4, R = 2 * MT;
     using O = ChainOff<KS1, NH, NO, BD>;
     const int g = lane >> 2, t = lane & 3;
@@ -234,8 +246,6 @@ HINT_DEV void c_node_fwd(const ChainNode* nd, float alpha, const float* __restri
     float s[NO][MT][4], tt[NO][MT][4];
     c_subnet<WS, MT, KS1, NH, NO, BD>(a1, Wn, lane, s);
     c_subnet<WS, MT, KS1, NH, NO, BD>(a1, Wn + O::net, lane, tt);
-    float jl[R];
-    c_ld_rows<MT>(JP + (t * 16 * MT) + R * g, jl);
 #pragma unroll
     for (int j = 0; j < NO; ++j)
 #pragma unroll
@@ -258,14 +268,13 @@ HINT_DEV void c_node_fwd(const ChainNode* nd, float alpha, const float* __restri
                 c_st_rows<MT>(xp, xv);
             }
         }
-    c_st_rows<MT>(JP + (t * 16 * MT) + R * g, jl);
 }
 
 #define HINT_CHAIN_SHAPES(X) X(0, 1, 1, 1, 0) X(1, 1, 2, 1, 1) X(2, 1, 4, 1, 1) X(3, 1, 2, 1, 0) X(4, 1, 3, 1, 0) \
                              X(5, 1, 5, 1, 0) X(6, 2, 5, 2, 0) X(7, 2, 9, 2, 0) X(8, 3, 9, 3, 0)
 
 template <bool WS, int MT, bool REV>
-HINT_DEV void c_node_fwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* XT, float* JP, int lane) {
+HINT_DEV void c_node_fwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* XT, float (&JP)[2 * MT], int lane) {
     const float* Wn = W + nd->w_off;
 #define HINT_CHAIN_CASE(ID, A, B, C, D) \
     case ID: c_node_fwd<WS, MT, A, B, C, D, REV>(nd, alpha, Wn, XT, JP, lane); break;
@@ -340,9 +349,9 @@ HINT_DEV void c_store_tile(const float* XT, int col_base, float* __restrict__ gd
     }
 }
 
-// floats of one warp's private shared-memory region (x + condition columns, 4 log-det partial rows)
+// floats of one warp's private shared-memory region (x + condition columns)
 template <int MT>
-HINT_HD constexpr int chain_fwd_warp_floats(int d, int dc) { return (d + dc) * (16 * MT + 4) + 4 * 16 * MT; }
+HINT_HD constexpr int chain_fwd_warp_floats(int d, int dc) { return (d + dc) * (16 * MT + 4); }
 
 template <int MT, int NW, bool REV, bool WS>
 HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S, const float* __restrict__ x, const float* __restrict__ c,
@@ -350,8 +359,8 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
                          int bid, int nblocks) {
     constexpr int RW = 16 * MT;
     const int warp = tid >> 5, lane = tid & 31;
+    constexpr int R = 2 * MT;
     float* XT = S + warp * chain_fwd_warp_floats<MT>(T.d, T.dc);
-    float* JP = XT + (T.d + T.dc) * (RW + 4);
     const long long ntiles = (B + RW - 1) / RW;
     // The warps are independent, but they all run the same (large, fully unrolled) instruction stream: a CTA barrier per
     // tile (T.exp & 8) or per node (T.exp & 16) keeps them in step so they share the instruction cache.
@@ -363,9 +372,11 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
         if (live) {
             c_load_tile<MT>(XT, 0, x, row0, rows, T.d, lane);
             c_load_tile<MT>(XT, T.d, c, row0, rows, T.dc, lane);
-            for (int i = lane; i < 4 * RW; i += 32) JP[i] = 0.f;
             c_syncwarp();
         }
+        float JP[R];      // the lane's log-det partials of its R rows (summed over the 4 lanes of a row group at the end)
+#pragma unroll
+        for (int e = 0; e < R; ++e) JP[e] = 0.f;
         for (int q = 0; q < T.n_nodes; ++q) {
             if (live) {
                 c_node_fwd_dispatch<WS, MT, REV>(nodes + (REV ? T.n_nodes - 1 - q : q), T.alpha, W, XT, JP, lane);
@@ -375,7 +386,13 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
         }
         if (live) {
             c_store_tile<MT>(XT, 0, z, row0, rows, T.d, lane);
-            if (lane < rows) logdet[row0 + lane] = JP[lane] + JP[RW + lane] + JP[2 * RW + lane] + JP[3 * RW + lane];
+#pragma unroll
+            for (int e = 0; e < R; ++e) {
+                JP[e] += c_shfl_xor(JP[e], 1);
+                JP[e] += c_shfl_xor(JP[e], 2);
+                const int row = R * (lane >> 2) + e;
+                if ((lane & 3) == 0 && row < rows) logdet[row0 + row] = JP[e];
+            }
             c_syncwarp();
         }
         if (T.exp & 8) m_cta_sync();

@@ -141,12 +141,7 @@ void build_chain_plan(const Plan& p, ChainPlan& c) {
                 const int64_t w3 = poff(p, i, net, 2, 0), b3 = poff(p, i, net, 2, 1);
                 auto set = [&](int64_t idx, int64_t src) { c.pack_src[(size_t)(base + idx)] = (int32_t)src; };
                 auto sett = [&](int64_t idx, int64_t src) { c.pack_src[(size_t)(tbase + idx)] = (int32_t)src; };
-                // bias u of an operand at `reg`: quad positions (u%2) and (u%2)+2 of the 16-float record of n-tile u/8
-                auto set_bias = [&](int64_t reg, int u, int64_t src) {
-                    const int64_t q = reg + (u >> 3) * 16 + ((u & 7) >> 1) * 4 + (u & 1);
-                    c.pack_src[(size_t)(base + q)] = (int32_t)(-src - 2);
-                    c.pack_src[(size_t)(base + q + 2)] = (int32_t)(-src - 2);
-                };
+                auto set_bias = [&](int64_t reg, int u, int64_t src) { c.pack_src[(size_t)(base + reg + u)] = (int32_t)(-src - 2); };
                 auto un = [&](int64_t param, int64_t idx) { c.unpack_src[(size_t)param] = (int32_t)(dbase + idx); };
                 for (int u = 0; u < nd.h; ++u) {
                     for (int f = 0; f < nd.cin; ++f) {

@@ -50,13 +50,12 @@ constexpr ChainShape kChainShapes[kChainNumShapes] = {{1, 1, 1, 0}, {1, 2, 1, 1}
 // kernel): per node two nets (s, t), each [W1 | b1 | W2 | b2 | W3 | b3].  Transposed region (dgrad GEMMs of the backward),
 // after the forward region: per node two nets, each [W3T | W2T | W1T].
 // W* are B-fragment ordered (k-step major, n-tile, lane, 2 floats; a block-diagonal W2 keeps its nh diagonal fragments);
-// b* are stored as the C-fragment quads that initialise the accumulators: per n-tile 4 x (b[2t], b[2t+1], b[2t], b[2t+1]),
-// so a lane fetches its quad with one 128-bit load.
+// b* natural order (a lane fetches (b[2t], b[2t+1]) of an n-tile with one 64-bit load: the C operand of the first k-step).
 template <int KS1, int NH, int NO, int BD>
 struct ChainOff {
     static constexpr int w2f = (BD ? NH : NH * NH) * 64;
-    static constexpr int w1 = 0, b1 = KS1 * NH * 64, w2 = b1 + NH * 16, b2 = w2 + w2f, w3 = b2 + NH * 16, b3 = w3 + NH * NO * 64;
-    static constexpr int net = b3 + NO * 16;                      // floats of one net in the forward region
+    static constexpr int w1 = 0, b1 = KS1 * NH * 64, w2 = b1 + NH * 8, b2 = w2 + w2f, w3 = b2 + NH * 8, b3 = w3 + NH * NO * 64;
+    static constexpr int net = b3 + NO * 8;                       // floats of one net in the forward region
     static constexpr int w3t = 0, w2t = NO * NH * 64, w1t = w2t + w2f;
     static constexpr int tnet = w1t + NH * KS1 * 64;              // ... in the transposed region
     // partial gradients of one net: [dW1T | dW2T | dW3T], dW_lT = [In | 1]^T dOut stored as C fragments (m-tile over IN
@@ -69,8 +68,8 @@ struct ChainOffRt { int w1, b1, w2, b2, w3, b3, net, w3t, w2t, w1t, tnet, dw1, d
 inline ChainOffRt chain_off(const ChainShape& s) {
     ChainOffRt o{};
     const int w2f = (s.bd ? s.nh : s.nh * s.nh) * 64;
-    o.w1 = 0; o.b1 = s.ks1 * s.nh * 64; o.w2 = o.b1 + s.nh * 16; o.b2 = o.w2 + w2f; o.w3 = o.b2 + s.nh * 16;
-    o.b3 = o.w3 + s.nh * s.no * 64; o.net = o.b3 + s.no * 16;
+    o.w1 = 0; o.b1 = s.ks1 * s.nh * 64; o.w2 = o.b1 + s.nh * 8; o.b2 = o.w2 + w2f; o.w3 = o.b2 + s.nh * 8;
+    o.b3 = o.w3 + s.nh * s.no * 64; o.net = o.b3 + s.no * 8;
     o.w3t = 0; o.w2t = s.no * s.nh * 64; o.w1t = o.w2t + w2f; o.tnet = o.w1t + s.nh * s.ks1 * 64;
     const int mt1 = (8 * s.ks1 + 1 + 15) / 16, mth = (8 * s.nh + 1 + 15) / 16;
     o.dw1 = 0; o.dw2 = mt1 * s.nh * 128; o.dw3 = o.dw2 + mth * s.nh * 128; o.dnet = o.dw3 + mth * s.no * 128;

@@ -26,6 +26,7 @@ struct WarpX {
     int count = 0;
     unsigned gen = 0;
     const float* rowp[32];
+    float shv[32];
     uint32_t a[32][4];
     uint32_t b[32][2];
 };
@@ -76,6 +77,17 @@ void ldsm4(const float* rowp, uint32_t (&r)[4]) {
     warp_rendezvous(w);
     for (int m = 0; m < 4; ++m) std::memcpy(&r[m], w.rowp[8 * m + (lane >> 2)] + (lane & 3), 4);
     warp_rendezvous(w);
+}
+
+float shfl_xor(float v, int mask) {
+    Cta* cta = g_cta;
+    const int lane = cta->cur & 31;
+    WarpX& w = cta->warps[cta->cur >> 5];
+    w.shv[lane] = v;
+    warp_rendezvous(w);
+    const float r = w.shv[lane ^ mask];
+    warp_rendezvous(w);
+    return r;
 }
 
 static inline float tf32(uint32_t u) {
