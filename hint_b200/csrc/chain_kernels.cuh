@@ -86,8 +86,8 @@ HINT_DEV void c_st_rows(float* p, const float (&v)[2 * MT]) {
 #endif
 }
 
-// d = a*b + c with c in its own registers: the bias quad of an n-tile is shared by all its m-tiles, so no accumulator is
-// ever initialised with moves
+// d = a*b + c with c in its own registers: the bias enters as the C operand of the first k-step, so no accumulator is ever
+// initialised with moves
 HINT_DEV void c_mma_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
 #if defined(__CUDA_ARCH__)
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
@@ -109,19 +109,6 @@ HINT_DEV void c_mma_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32
     m_mma(d, a, b0, b1);
 #endif
 }
-// the lane's bias quad of n-tile j: (b[2t], b[2t+1], b[2t], b[2t+1]) stored contiguously
-template <bool WS>
-HINT_DEV void c_ldb4(const float* __restrict__ p, float (&c)[4]) {
-#if defined(__CUDA_ARCH__)
-    float4 v;
-    if (WS) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    else v = __ldg(reinterpret_cast<const float4*>(p));
-    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
-#else
-    for (int e = 0; e < 4; ++e) c[e] = p[e];
-#endif
-}
-
 HINT_DEV uint32_t c_relu_rna(float v) { return m_bits(fmaxf(v, 0.f)) + 0x1000u; }
 
 // One dense layer in registers: out[MT][NT_OUT] C fragments = bias + A[KS k-steps] * B.  B fragments (KS x NT_OUT) at Wl,
