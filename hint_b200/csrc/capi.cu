@@ -216,6 +216,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
     }
     build_mma_plan(hp->p, hp->mma);
     build_chain_plan(hp->p, hp->chain);
+    if (hp->chain.ok && !chain_fits(hp->p, hp->chain, &hp->chain.why)) hp->chain.ok = false;
     build_tc_schedule(hp->p, hp->tc);
     build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "chain_kernels.cuh"
@@ -80,6 +81,13 @@ cudaError_t upload(T** dst, const std::vector<T>& v) {
 }
 
 }  // namespace
+
+bool chain_fits(const Plan& p, const ChainPlan& c, std::string* why) {
+    const size_t f = fwd_smem(p, c, 1, 16, 0), b = (size_t)bwd_layout(p, c, pick_bwd()).total * 4;
+    if (f <= (size_t)kSmemMax && b <= (size_t)kSmemMax) return true;
+    if (why) *why = "tile state of the register-chained kernels (" + std::to_string(std::max(f, b)) + " B) exceeds shared memory";
+    return false;
+}
 
 cudaError_t chain_setup(const Plan& p, const ChainPlan& c, int num_sms, DevChain& d) {
     cudaError_t e;

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <string>
+
 #include "plan_chain.h"
 
 namespace hint {
@@ -16,6 +18,8 @@ struct DevChain {
     int bwd_mt = 1, bwd_nw = 4;
 };
 
+// host-side envelope check: the tile state of the forward (L1 configuration) and backward kernels must fit shared memory
+bool chain_fits(const Plan& p, const ChainPlan& c, std::string* why);
 cudaError_t chain_setup(const Plan& p, const ChainPlan& c, int num_sms, DevChain& d);
 void chain_free(DevChain& d);
 cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* params, float* packed, cudaStream_t st);
