@@ -80,3 +80,43 @@ def test_outside_envelope_is_reported():
     g = load_golden("wide_h_d12")
     with pytest.raises(LookupError):
         emul_chain_lib.run(*_args(g), g["x"], g.get("c"), mt=1)
+
+
+def _random_cfg(rng):
+    d = int(rng.integers(2, 30))
+    dc = int(rng.choice([0, 0, 1, 3]))
+    n_w = int(rng.integers(1, 5))
+    widths = [int(rng.integers(3, 41)) for _ in range(n_w)]
+    ms = int(rng.choice([-1, -1, 0, 1, 2, 3]))
+    mss = int(rng.choice([2, 2, 3, 4]))
+    return d, dc, widths, ms, mss
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_trees_against_the_oracle(seed):
+    """Random tree shapes (odd widths, conditions, split limits): planner grouping / packing / column maps of the chain kernels
+    against the fp64 oracle (oracle/hint_oracle.py, itself pinned to the real hint.py by the golden vectors)."""
+    import torch
+    from oracle import hint_oracle as O
+    rng = np.random.default_rng(1000 + seed)
+    d, dc, widths, ms, mss = _random_cfg(rng)
+    plan = O.build_plan(d, dc, widths, ms, mss)
+    n = O.param_count(plan)
+    params = (0.3 * rng.standard_normal(n)).astype(np.float32)
+    B = int(rng.integers(1, 70))
+    x = rng.standard_normal((B, d)).astype(np.float32)
+    c = rng.standard_normal((B, dc)).astype(np.float32) if dc else None
+    p64 = torch.from_numpy(params).double()
+    c64 = None if c is None else torch.from_numpy(c).double()
+    z_ref, J_ref = O.forward_fast(plan, p64, torch.from_numpy(x).double(), c64)
+    dz = torch.from_numpy(rng.standard_normal((B, d))).double() / B
+    dJ = torch.from_numpy(rng.standard_normal(B)).double() / B
+    _, dx_ref, dc_ref, dp_ref = O.backward_from_output(plan, p64, z_ref, c64, dz, dJ)
+    try:
+        out = emul_chain_lib.run(d, dc, widths, 4.0, ms, mss, params, x, c, backward=(dz.numpy(), dJ.numpy()), mt=1 + seed % 3, nctas=2)
+    except LookupError:
+        pytest.skip("outside the chain envelope")
+    assert _rel(out["z"], z_ref.numpy()) < TF32_TOL and _rel(out["J"], J_ref.numpy()) < TF32_TOL
+    assert _l2(out["dx"], dx_ref.numpy()) < 2e-2 and _l2(out["dparams"], dp_ref.numpy()) < 2e-2
+    if dc:
+        assert _l2(out["dc"], dc_ref.numpy()) < 3e-2

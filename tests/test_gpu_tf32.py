@@ -203,3 +203,52 @@ def test_full_size_properties_chain():
     assert (dx2 - 2 * dx1).abs().max().item() <= 1e-5 * dx1.abs().max().item() + 1e-9
     rel = lambda a, b: (torch.linalg.norm(a.double() - b.double()) / torch.linalg.norm(b.double())).item()
     assert rel(g1, gf) < 2e-2 and rel(dx1, dxf) < 2e-2
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_trees_chain_against_the_oracle(seed):
+    """Random tree shapes through the C ABI in the register-chained mode (forward, inverse, backward) against the fp64 oracle."""
+    rng = np.random.default_rng(7000 + seed)
+    d = int(rng.integers(2, 48))
+    dc = int(rng.choice([0, 0, 1, 3]))
+    widths = [int(rng.integers(3, 73)) for _ in range(int(rng.integers(1, 5)))]
+    ms = int(rng.choice([-1, -1, 0, 1, 2, 3]))
+    mss = int(rng.choice([2, 2, 3, 4]))
+    B = int(rng.integers(1, 700))
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    dev = torch.device("cuda:0")
+    torch.manual_seed(seed)
+    blk = HierarchicalAffineCouplingBlock([(d,)], dims_c=[(dc,)] if dc else [], c_internal=widths, max_splits=ms, min_split_size=mss)
+    if not blk.plan.mode_supported("tf32_chain"):
+        pytest.skip("outside the chain envelope")
+    with torch.no_grad():
+        blk.flat.mul_(0.4)
+    flat64 = blk.flat.detach().double().clone()
+    blk = blk.to(dev)
+    x = torch.randn(B, d)
+    c = torch.randn(B, dc) if dc else None
+    plan = O.build_plan(d, dc, widths, ms, mss)
+    c64 = None if c is None else c.double()
+    z_ref, J_ref = O.forward_fast(plan, flat64, x.double(), c64)
+    dz = torch.randn(B, d, dtype=torch.float64) / B
+    dJ = torch.randn(B, dtype=torch.float64) / B
+    _, dx_ref, dc_ref, dflat_ref = O.backward_from_output(plan, flat64, z_ref, c64, dz, dJ)
+    cg = c.to(dev) if dc else None
+    with torch.no_grad():
+        z, J = blk.plan.forward(x.to(dev), cg, blk.flat.detach(), mode="tf32_chain")
+        xr, Jr = blk.plan.forward(z, cg, blk.flat.detach(), rev=True, mode="tf32_chain")
+        dx, dcc, dflat, _ = blk.plan.backward(z_ref.float().to(dev), cg, blk.flat.detach(), dz.float().to(dev), dJ.float().to(dev),
+                                              mode="tf32_chain")
+    assert _err(z, z_ref.numpy()) < TF32_TOL and _err(J, J_ref.numpy()) < TF32_TOL
+    assert _err(xr, x.double().numpy()) < TF32_TOL * max(1.0, float(z_ref.abs().max()))
+    # gradients: TF32 rounding noise grows with the weight scale of wide subnets (ReLU kinks flip for isolated samples), so the
+    # bound against the fp64 oracle is loose; the sharp check is agreement with the interpreter warp-MMA kernels, which round at
+    # the same points through completely different code
+    assert _l2(dx, dx_ref.numpy()) < 4e-2 and _l2(dflat, dflat_ref.numpy()) < 4e-2
+    if dc:
+        assert _l2(dcc, dc_ref.numpy()) < 4e-2
+    if blk.plan.mode_supported("tf32_mma"):
+        with torch.no_grad():
+            dx2, dc2, dflat2, _ = blk.plan.backward(z_ref.float().to(dev), cg, blk.flat.detach(), dz.float().to(dev), dJ.float().to(dev),
+                                                    mode="tf32_mma")
+        assert _l2(dx, dx2.double().cpu().numpy()) < 2e-3 and _l2(dflat, dflat2.double().cpu().numpy()) < 2e-3
