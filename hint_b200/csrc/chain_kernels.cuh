@@ -436,6 +436,16 @@ hint_fwd_chain_kernel(const __grid_constant__ ChainTables T, const __grid_consta
 //   barrier.
 HINT_DEV int c_swz(int col) { return col & 7; }
 
+// two matrices (lanes 0-15 supply the row addresses): one B fragment
+HINT_DEV void c_ldsm2(const float* rowp, uint32_t (&r)[4]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(rowp)) : "memory");
+#elif !defined(__CUDACC__)
+    emu::ldsm4(rowp, r);
+#endif
+}
+
 // developer aid (T.exp & 32): thread 0 of CTA 0 records clock64 at the phase boundaries of the backward sweep
 #if defined(__CUDACC__)
 __device__ long long g_chain_dbg[2048];
@@ -599,14 +609,20 @@ HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff,
         uint32_t a[2][4], b[2][NP][4];
         c_ldsm4(S + abase, a[0]);
 #pragma unroll
-        for (int p = 0; p < NP; ++p) c_ldsm4(S + bbase[p], b[0][p]);
+        for (int p = 0; p < NP; ++p) {
+            if (2 * p + 1 < NC) c_ldsm4(S + bbase[p], b[0][p]);
+            else c_ldsm2(S + bbase[p], b[0][p]);       // odd last n-tile: half the fetch
+        }
 #pragma unroll
         for (int ks = 0; ks < TM / 8; ++ks) {
             const int cur = ks & 1, nxt = cur ^ 1;
             if (ks + 1 < TM / 8) {
                 c_ldsm4(S + (abase ^ (((ks + 1) << 3) & amask)), a[nxt]);
 #pragma unroll
-                for (int p = 0; p < NP; ++p) c_ldsm4(S + (bbase[p] ^ (((ks + 1) << 3) & bmask[p])), b[nxt][p]);
+                for (int p = 0; p < NP; ++p) {
+                    if (2 * p + 1 < NC) c_ldsm4(S + (bbase[p] ^ (((ks + 1) << 3) & bmask[p])), b[nxt][p]);
+                    else c_ldsm2(S + (bbase[p] ^ (((ks + 1) << 3) & bmask[p])), b[nxt][p]);
+                }
             }
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
