@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhint_b200.so")
 
 HINT_OK, HINT_ERR_INVALID, HINT_ERR_UNSUPPORTED, HINT_ERR_CUDA, HINT_ERR_WORKSPACE = 0, 1, 2, 3, 4
-MODE_FP32, MODE_TF32, MODE_TF32X3, MODE_TF32_TCGEN05, MODE_TF32_MMA, MODE_TF32_CHAIN = 0, 1, 2, 3, 4, 5
+MODE_FP32, MODE_TF32, MODE_TF32X3, MODE_TF32_TCGEN05, MODE_TF32_MMA, MODE_TF32_CHAIN, MODE_TF32_TC3 = 0, 1, 2, 3, 4, 5, 6
 WS_FORWARD, WS_BACKWARD = 0, 1
 
 # every symbol include/hint_b200.h declares (tests/test_capi.py checks the header against this list)

@@ -19,7 +19,8 @@ import torch.nn as nn
 from . import _lib
 
 _MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "tf32x3": _lib.MODE_TF32X3, "3xtf32": _lib.MODE_TF32X3,
-          "tf32_tcgen05": _lib.MODE_TF32_TCGEN05, "tf32_mma": _lib.MODE_TF32_MMA, "tf32_chain": _lib.MODE_TF32_CHAIN}
+          "tf32_tcgen05": _lib.MODE_TF32_TCGEN05, "tf32_mma": _lib.MODE_TF32_MMA, "tf32_chain": _lib.MODE_TF32_CHAIN,
+          "tf32_tc3": _lib.MODE_TF32_TC3}
 _mode = os.environ.get("HINT_B200_MODE", "fp32").lower()
 
 

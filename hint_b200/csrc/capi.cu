@@ -16,6 +16,8 @@
 #include "mma_launch.h"
 #include "plan_chain.h"
 #include "chain_launch.h"
+#include "plan_tc3.h"
+#include "tc3_launch.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc2_kernels.cuh"
@@ -60,6 +62,7 @@ struct DevPlan {
     DevTc tc;
     DevMma mma;
     DevChain chain;
+    DevTc3 tc3;
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
     int num_sms = 0;
@@ -71,6 +74,7 @@ struct hint_plan {
     Plan p;
     MmaPlan mma;
     ChainPlan chain;
+    T3Plan tc3;
     TcSchedule tc;
     T2Host tc2;
     std::mutex mu;
@@ -141,6 +145,9 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     if (hp->chain.ok) {
         CUDA_TRY(chain_setup(hp->p, hp->chain, d.num_sms, d.chain));
     }
+    if (hp->tc3.ok) {
+        CUDA_TRY(tc3_setup(hp->tc3, d.num_sms, d.tc3));
+    }
     if (hp->tc.ok) {
         CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
         CUDA_TRY(upload(&d.tc.ops, hp->tc.ops));
@@ -201,6 +208,27 @@ size_t mma_packed_bytes(const MmaPlan& m) { return 2 * mma_half_bytes(m); }
 extern "C" {
 
 const char* hint_last_error(void) { return g_err.c_str(); }
+
+// Developer entry point (not part of include/hint_b200.h): step-limited single-tile run of the tcgen05 training kernel with a
+// dump of TMEM and shared memory, compared step by step against tests/emul/emul_tc3.cpp by tests/cuda/dbg_tc3.py.
+int hint_dev_tc3_debug(hint_plan_t* hp, int32_t n_epi_limit, const float* z, const float* c, const float* params, const float* dz,
+                       const float* dlogdet, int64_t B, float* x_rec, float* dx, float* dc, float* dump, int32_t* layout, void* workspace,
+                       void* stream) {
+    if (!hp || !hp->tc3.ok) return fail(HINT_ERR_UNSUPPORTED, "no tc3 plan");
+    DevPlan* d = nullptr;
+    int rc = get_dev(hp, &d);
+    if (rc != HINT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* packed = reinterpret_cast<float*>(workspace);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((hp->tc3.n_packed * 4 + 255) & ~255ll));
+    CUDA_TRY(tc3_pack(hp->tc3, d->tc3, params, packed, st));
+    CUDA_TRY(tc3_debug_run(hp->tc3, d->tc3, n_epi_limit, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, (long long)B, dump, st));
+    const T3Plan& t = hp->tc3;
+    int32_t L[] = {t.sm_xs, t.sm_gs, t.sm_os, t.xp, t.op, t.sm_img[0], t.sm_img[1], t.sm_img[2], t.sm_img[3], t.sm_img[4],
+                   t.img_rows[0], t.img_rows[1], t.img_rows[2], t.img_rows[3], t.img_rows[4], (int32_t)t.epis.size(), t.sm_red};
+    for (size_t i = 0; i < sizeof(L) / 4; ++i) layout[i] = L[i];
+    return HINT_OK;
+}
 const char* hint_version(void) { return "hint_b200 0.1 sm_100a"; }
 
 int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n_internal, double clamp,
@@ -217,6 +245,7 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
     build_mma_plan(hp->p, hp->mma);
     build_chain_plan(hp->p, hp->chain);
     if (hp->chain.ok && !chain_fits(hp->p, hp->chain, &hp->chain.why)) hp->chain.ok = false;
+    build_tc3_plan(hp->p, hp->tc3);
     build_tc_schedule(hp->p, hp->tc);
     build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
@@ -236,6 +265,7 @@ void hint_plan_destroy(hint_plan_t* hp) {
         cudaFree(d.pack_src); cudaFree(d.unpack_src);
         mma_free(d.mma);
         chain_free(d.chain);
+        tc3_free(d.tc3);
         cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
@@ -273,6 +303,7 @@ int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
         case HINT_MODE_TF32: case HINT_MODE_TF32X3: case HINT_MODE_TF32_MMA: return hp->mma.ok ? 1 : 0;
         case HINT_MODE_TF32_TCGEN05: return hp->tc.ok ? 1 : 0;
         case HINT_MODE_TF32_CHAIN: return (hp->chain.ok && hp->mma.ok) ? 1 : 0;
+        case HINT_MODE_TF32_TC3: return (hp->tc3.ok && hp->mma.ok) ? 1 : 0;
     }
     return 0;
 }
@@ -283,12 +314,14 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     size_t bytes = align256((size_t)std::max<long long>(hp->p.n_packed, hp->tc.ok ? hp->tc.n_packed : 0) * 4);
     if (hp->mma.ok) bytes = std::max(bytes, mma_packed_bytes(hp->mma));
     if (hp->chain.ok) bytes = std::max(bytes, align256((size_t)hp->chain.n_packed * 4));
+    if (hp->tc3.ok) bytes = std::max(bytes, align256((size_t)hp->tc3.n_packed * 4));
     if (which == HINT_WS_BACKWARD) {
         DevPlan* d = nullptr;
         if (get_dev(hp, &d) != HINT_OK) return 0;
         size_t part = align256((size_t)bwd_ctas(hp->p, *d, B) * (size_t)hp->p.n_partial * 4);
         if (hp->mma.ok) part = std::max(part, align256((size_t)mma_bwd_ctas(hp->mma, *d, B) * (size_t)hp->mma.n_partial * 4));
         if (hp->chain.ok) part = std::max(part, align256((size_t)chain_bwd_ctas(hp->chain, d->chain, B) * (size_t)hp->chain.n_partial * 4));
+        if (hp->tc3.ok) part = std::max(part, align256((size_t)tc3_bwd_ctas(d->tc3, B) * (size_t)hp->tc3.n_partial * 4));
         bytes += part;
     }
     return bytes + 256;
@@ -298,8 +331,11 @@ static int check_common(const hint_plan* hp, const float* x, const float* c, con
     if (!hp) return fail(HINT_ERR_INVALID, "plan is NULL");
     if (B < 0) return fail(HINT_ERR_INVALID, "negative batch");
     if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32 && mode != HINT_MODE_TF32X3 && mode != HINT_MODE_TF32_TCGEN05 &&
-        mode != HINT_MODE_TF32_MMA && mode != HINT_MODE_TF32_CHAIN)
+        mode != HINT_MODE_TF32_MMA && mode != HINT_MODE_TF32_CHAIN && mode != HINT_MODE_TF32_TC3)
         return fail(HINT_ERR_INVALID, "unknown mode");
+    if (mode == HINT_MODE_TF32_TC3 && !hp->tc3.ok)
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the tcgen05 training kernel's envelope: " + hp->tc3.why);
+    if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // forward / inverse: the TF32 default
     if (mode == HINT_MODE_TF32_CHAIN && !hp->chain.ok)
         return fail(HINT_ERR_UNSUPPORTED, "this block is outside the register-chained kernels' envelope: " + hp->chain.why);
     if (mode == HINT_MODE_TF32_CHAIN) mode = HINT_MODE_TF32_MMA;   // same requirements otherwise
@@ -332,6 +368,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     // block fits its TMEM envelope (measured 1.9 ms vs 4.0 ms per 2^20 samples on the d=43 hint_8 block), the warp-MMA kernel
     // covers the rest.  HINT_B200_TF32_FWD=mma|tcgen05 forces one; HINT_MODE_TF32_MMA / HINT_MODE_TF32_TCGEN05 name them
     // explicitly (tests run both).
+    if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // the training kernel's mode: forward / inverse as in HINT_MODE_TF32
     if (mode == HINT_MODE_TF32) {
         static const char* pref = std::getenv("HINT_B200_TF32_FWD");
         const bool want_chain = pref ? std::strcmp(pref, "chain") == 0 : true;
@@ -467,6 +504,14 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
     if (!workspace || workspace_bytes < hint_workspace_bytes(hp, B, HINT_WS_BACKWARD))
         return fail(HINT_ERR_WORKSPACE, "workspace too small");
     float* packed = reinterpret_cast<float*>(workspace);
+    // tcgen05 training kernel: explicit mode, and the HINT_MODE_TF32 default for blocks the register-chained kernels do not cover
+    if (mode == HINT_MODE_TF32_TC3 || (mode == HINT_MODE_TF32 && !use_chain && hp->tc3.ok)) {
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->tc3.n_packed * 4));
+        CUDA_TRY(tc3_pack(hp->tc3, d->tc3, params, packed, st));
+        const int grid = tc3_bwd_ctas(d->tc3, (long long)B);
+        CUDA_TRY(tc3_launch_bwd(hp->tc3, d->tc3, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, dparams, (long long)B, st));
+        return HINT_OK;
+    }
     if (use_chain) {
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->chain.n_packed * 4));
         CUDA_TRY(chain_pack(hp->chain, d->chain, params, packed, st));

@@ -46,6 +46,10 @@ extern "C" {
 #define HINT_MODE_TF32_CHAIN 5  /* HINT_MODE_TF32 with the register-chained warp-MMA kernels forced (HINT_MODE_TF32 picks
                                    them whenever the block fits their shape table)                                   */
 
+#define HINT_MODE_TF32_TC3 6    /* HINT_MODE_TF32 with the tcgen05 / TMEM training kernel forced for the backward (tensor-memory
+                                   accumulators, weight gradients as tcgen05.mma over shared-memory images); HINT_MODE_TF32 picks
+                                   it for the blocks the register-chained kernels do not cover                           */
+
 /* which workspace hint_workspace_bytes() sizes */
 #define HINT_WS_FORWARD 0
 #define HINT_WS_BACKWARD 1
