@@ -209,6 +209,28 @@ extern "C" {
 
 const char* hint_last_error(void) { return g_err.c_str(); }
 
+// Developer entry point: the regular tc3 backward launch with a timeline of CTA 0's second tile written to `prof`
+// (long long[4096]: [0,1024) issue clock of every MMA record, [1024,2048) arrival clocks of the epilogue steps of warps 0 / 4,
+// [2048, ...) clock at which warp 0 passed the step's wait).  Read by tests/cuda/prof_tc3.py.
+int hint_dev_tc3_profile(hint_plan_t* hp, const float* z, const float* c, const float* params, const float* dz, const float* dlogdet,
+                         int64_t B, float* dx, float* dc, float* dparams, long long* prof, int32_t* info, void* workspace, void* stream) {
+    if (!hp || !hp->tc3.ok) return fail(HINT_ERR_UNSUPPORTED, "no tc3 plan");
+    DevPlan* d = nullptr;
+    int rc = get_dev(hp, &d);
+    if (rc != HINT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* packed = reinterpret_cast<float*>(workspace);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((hp->tc3.n_packed * 4 + 255) & ~255ll));
+    CUDA_TRY(tc3_pack(hp->tc3, d->tc3, params, packed, st));
+    const int grid = tc3_bwd_ctas(d->tc3, (long long)B);
+    CUDA_TRY(tc3_launch_bwd(hp->tc3, d->tc3, grid, z, c, packed, dz, dlogdet, nullptr, dx, dc, partials, dparams, (long long)B, st, prof));
+    const T3Plan& t = hp->tc3;
+    info[0] = (int32_t)t.mmas.size(); info[1] = (int32_t)t.epis.size(); info[2] = (int32_t)t.n_mma_instr; info[3] = (int32_t)t.tensor_cycles;
+    for (size_t i = 0; i < t.epis.size() && i < 512; ++i) info[16 + i] = t.epis[i].type | (t.epis[i].wait_mma << 8);
+    for (size_t i = 0; i < t.mmas.size() && i < 1024; ++i) info[1024 + i] = (int32_t)t.mmas[i].nk | ((int32_t)t.mmas[i].flags << 8) | ((int32_t)(((t.mmas[i].idesc >> 17) & 63) << 3) << 16);
+    return HINT_OK;
+}
+
 // Developer entry point (not part of include/hint_b200.h): step-limited single-tile run of the tcgen05 training kernel with a
 // dump of TMEM and shared memory, compared step by step against tests/emul/emul_tc3.cpp by tests/cuda/dbg_tc3.py.
 int hint_dev_tc3_debug(hint_plan_t* hp, int32_t n_epi_limit, const float* z, const float* c, const float* params, const float* dz,

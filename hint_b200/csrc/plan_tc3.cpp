@@ -147,17 +147,17 @@ struct Builder {
             int w = -1;
             for (int m = 0; m < nm; ++m)
                 if (mtime[m] < etime[e] && conflicts(eacc[e], macc[m])) w = std::max(w, sig[m]);
-            t.epis[e].wait_mma = (int16_t)w;
+            t.epis[e].wait_mma = w;
         }
         for (int m = 0; m < nm; ++m) {
             int w = -1;
             for (int e = 0; e < ne; ++e)
                 if (etime[e] < mtime[m] && conflicts(macc[m], eacc[e])) w = std::max(w, e);
-            t.mmas[m].wait_epi = (int16_t)w;
+            t.mmas[m].wait_epi = w;
         }
         // a wait that an earlier step of the same role already implies is redundant but harmless; keep the tables simple.
         // tile boundary: the last epilogue step drains the tensor pipe, so the next tile starts from a clean state
-        if (ne) t.epis[ne - 1].wait_mma = (int16_t)(t.n_mma_signals - 1);
+        if (ne) t.epis[ne - 1].wait_mma = (t.n_mma_signals - 1);
     }
 };
 
@@ -237,7 +237,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
 
     // ---- shared memory map ----
     t.xp = (p.d + p.dc) | 1;
-    int HPmax = 0, N1max = 0, N2max = 0, OCmax = 0, OWmax = 0, mtmax = 1;
+    int HPmax = 0, N1max = 0, N2max = 0, OCmax = 0, OWmax = 0, mtmax = 1, tab_bytes = 0, epi_bytes = 0;
     auto layout = [&](int nimg, int nslots, int slot) {
         int o = 0;
         t.sm_bars = o; o += 1024;
@@ -253,7 +253,8 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         t.sm_img[3] = o; t.img_rows[3] = pad8(N1max); o += t.img_rows[3] * 512;
         t.sm_img[4] = o; t.img_rows[4] = pad8(OWmax); o += t.img_rows[4] * 512;
         t.sm_ring = o; o += nslots * slot;
-        t.sm_tab16 = o; o += 4096;
+        t.sm_tab16 = o; o += tab_bytes;
+        t.sm_epis = o; o += epi_bytes;
         t.sm_xs = o; o += 128 * t.xp * 4;
         t.sm_gs = o; o += 128 * t.xp * 4;
         t.sm_os = o; o += 128 * t.op * 4;
@@ -271,6 +272,12 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
     bool placed = false;
     for (int hp_cap : {128, 112, 96, 80, 64, 48, 32}) {
         if (!build_groups(hp_cap)) return;   // `why` already set: no cap helps
+        tab_bytes = 0; epi_bytes = 0;
+        for (const T3Group& g : t.groups) {
+            tab_bytes += 2 * (g.KA + g.OC + g.KX + p.dc + 1 + 6 * (int)g.nodes.size());
+            epi_bytes += (int)sizeof(T3Epi) * (16 + 6 * g.mtiles);   // steps of one group: 4 + 9 + 9 plus the flushes of the extra M tiles
+        }
+        tab_bytes = (tab_bytes + 15) & ~15;
         HPmax = N1max = N2max = OCmax = OWmax = 0; mtmax = 1;
         for (const T3Group& g : t.groups) {
             HPmax = std::max(HPmax, g.HP); N1max = std::max(N1max, g.N1); N2max = std::max(N2max, g.N2);
@@ -283,6 +290,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
 
     // ---- partial-gradient layout + unpack map ----
     t.unpack_src.assign((size_t)p.n_params, -1);
+    t.unpack_q4.assign((size_t)p.n_params, 0);
     {
         int64_t o = 0;
         for (T3Group& g : t.groups) {
@@ -291,7 +299,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
                 g.part[net][0] = (int)o; o += (int64_t)rows * g.N2;
                 g.part[net][1] = (int)o; o += (int64_t)rows * g.N1;
                 g.part[net][2] = (int)o; o += (int64_t)rows * g.OW;
-                g.part[net][3] = (int)o; o += g.OW;
+                g.part[net][3] = (int)o; o += 4 * 32;   // layer-3 bias gradients: one slot per lane quadrant (deterministic, no atomics)
                 // accumulator blocks are stored lane-fastest ([M tile][column][128 lanes]): the flush (thread = lane) is coalesced
                 auto at = [&](int blk, int N, int row, int col) { return g.part[net][blk] + (row / 128) * (N * 128) + col * 128 + (row % 128); };
                 for (size_t q = 0; q < g.nodes.size(); ++q) {
@@ -312,6 +320,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
                         for (int m = 0; m < n.h; ++m)
                             t.unpack_src[(size_t)(poffc(p, ni, net, 2, 0) + (int64_t)c * n.h + m)] = at(2, g.OW, ho + m, oo + c);
                         t.unpack_src[(size_t)(poffc(p, ni, net, 2, 1) + c)] = g.part[net][3] + oo + c;
+                        t.unpack_q4[(size_t)(poffc(p, ni, net, 2, 1) + c)] = 1;
                     }
                 }
             }
@@ -330,16 +339,16 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         const int P = g.tm_p, Q = g.tm_q;
         // tables of this group
         std::vector<int16_t> in_src(g.KA, -1), out_x(g.OC, 0), da_dst(g.KX + p.dc, 0), ntab;
-        ntab.push_back((int16_t)nn);
+        ntab.push_back(nn);
         for (int q = 0; q < nn; ++q) {
             const auto& n = p.nodes[g.nodes[q]];
-            for (int m = 0; m < n.k; ++m) { in_src[g.xoff[q] + m] = (int16_t)(n.lo + m); da_dst[g.xoff[q] + m] = (int16_t)(n.lo + m); }
-            for (int c = 0; c < n.cout; ++c) out_x[g.ooff[q] + c] = (int16_t)(n.lo + n.k + c);
-            ntab.push_back((int16_t)g.hoff[q]); ntab.push_back((int16_t)n.h);
-            ntab.push_back((int16_t)g.xoff[q]); ntab.push_back((int16_t)n.k);
-            ntab.push_back((int16_t)g.ooff[q]); ntab.push_back((int16_t)n.cout);
+            for (int m = 0; m < n.k; ++m) { in_src[g.xoff[q] + m] = (n.lo + m); da_dst[g.xoff[q] + m] = (n.lo + m); }
+            for (int c = 0; c < n.cout; ++c) out_x[g.ooff[q] + c] = (n.lo + n.k + c);
+            ntab.push_back(g.hoff[q]); ntab.push_back(n.h);
+            ntab.push_back(g.xoff[q]); ntab.push_back(n.k);
+            ntab.push_back(g.ooff[q]); ntab.push_back(n.cout);
         }
-        for (int q2 = 0; q2 < p.dc; ++q2) { in_src[g.KX + q2] = (int16_t)(p.d + q2); da_dst[g.KX + q2] = (int16_t)(p.d + q2); }
+        for (int q2 = 0; q2 < p.dc; ++q2) { in_src[g.KX + q2] = (p.d + q2); da_dst[g.KX + q2] = (p.d + q2); }
         in_src[g.KX + p.dc] = -2;
         const int tab_in = b.tab(in_src), tab_out = b.tab(out_x), tab_da = b.tab(da_dst);
         g.tab_nodes = b.tab(ntab);
@@ -407,13 +416,13 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
 
         // ---- emitters ----
         auto e_in = [&]() {
-            T3Epi e{}; e.type = T3E_IN; e.a = (int16_t)tab_in; e.b = (int16_t)g.KA; e.c = (int16_t)g.tm_ain;
+            T3Epi e{}; e.type = T3E_IN; e.a = tab_in; e.b = g.KA; e.c = g.tm_ain;
             Acc a; a.wr.push_back({R_TMEM, g.tm_ain, g.tm_ain + g.KA}); a.wr.push_back({R_IMG0 + IMG_IN, 0, g.KA});
             b.push_epi(e, a);
         };
         auto e_hid = [&](int col0, int img, bool img_ones) {   // img < 0: no image
-            T3Epi e{}; e.type = T3E_HID; e.flags = (uint8_t)(T3H_ONES | (img >= 0 ? T3H_IMG : 0) | (img >= 0 && img_ones ? T3H_IMG_ONES : 0));
-            e.a = (int16_t)col0; e.b = (int16_t)g.HP; e.c = (int16_t)(img < 0 ? 0 : img);
+            T3Epi e{}; e.type = T3E_HID; e.flags = (T3H_ONES | (img >= 0 ? T3H_IMG : 0) | (img >= 0 && img_ones ? T3H_IMG_ONES : 0));
+            e.a = col0; e.b = g.HP; e.c = (img < 0 ? 0 : img);
             Acc a; a.rd.push_back({R_TMEM, col0, col0 + g.HP}); a.wr.push_back({R_TMEM, col0, col0 + g.HP + 8});
             if (img >= 0) a.wr.push_back({R_IMG0 + img, 0, g.HP + (img_ones ? 8 : 0)});
             b.push_epi(e, a);
@@ -422,9 +431,9 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             const int col0 = kind == T3F_W2 ? g.tm_acc2 : kind == T3F_W1 ? g.tm_acc1 : g.tm_acc3;
             const int N = kind == T3F_W2 ? g.N2 : kind == T3F_W1 ? g.N1 : g.OW;
             const int blk = kind == T3F_W2 ? 0 : kind == T3F_W1 ? 1 : 2;
-            T3Epi e{}; e.type = T3E_FLUSH; e.a = (int16_t)col0; e.b = (int16_t)N; e.off = g.part[net][blk] + mt * 128 * N; e.d = 128;
-            e.e = (int16_t)std::min(128, g.HP - mt * 128); e.f = (int16_t)g.tab_nodes; e.g = (int16_t)kind; e.h = (int16_t)mt;
-            e.c = (int16_t)(kind == T3F_W2 ? g.HP : kind == T3F_W1 ? g.KX : -1);   // first "extra" column (bias / condition block)
+            T3Epi e{}; e.type = T3E_FLUSH; e.a = col0; e.b = N; e.off = g.part[net][blk] + mt * 128 * N; e.d = 128;
+            e.e = std::min(128, g.HP - mt * 128); e.f = g.tab_nodes; e.g = kind; e.h = mt;
+            e.c = (kind == T3F_W2 ? g.HP : kind == T3F_W1 ? g.KX : -1);   // first "extra" column (bias / condition block)
             Acc a; a.rd.push_back({R_TMEM, col0, col0 + N});
             b.push_epi(e, a);
         };
@@ -446,7 +455,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             for (int mt = 0; mt < g.mtiles; ++mt) {
                 b.gemm_ss(IMG_H2, mt * 16, IMG_DOUT, g.OW, g.tm_acc3);
                 if (mt == g.mtiles - 1) {
-                    T3Epi d{}; d.type = T3E_DHID; d.flags = T3D_MASK_TMEM; d.a = (int16_t)P; d.b = (int16_t)g.HP; d.c = (int16_t)IMG_DH2; d.e = (int16_t)Q;
+                    T3Epi d{}; d.type = T3E_DHID; d.flags = T3D_MASK_TMEM; d.a = P; d.b = g.HP; d.c = IMG_DH2; d.e = Q;
                     Acc da; da.rd.push_back({R_TMEM, P, P + g.HP}); da.rd.push_back({R_TMEM, Q, Q + g.HP});
                     da.wr.push_back({R_TMEM, P, P + g.HP}); da.wr.push_back({R_IMG0 + IMG_DH2, 0, g.HP});
                     b.push_epi(d, da);
@@ -462,7 +471,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             for (int mt = 0; mt < g.mtiles; ++mt) {
                 b.gemm_ss(IMG_DH2, mt * 16, IMG_H1, g.N2, g.tm_acc2);
                 if (mt == g.mtiles - 1) {
-                    T3Epi d{}; d.type = T3E_DHID; d.flags = 0; d.a = (int16_t)Q; d.b = (int16_t)g.HP; d.c = (int16_t)IMG_DH1; d.e = (int16_t)IMG_H1;
+                    T3Epi d{}; d.type = T3E_DHID; d.flags = 0; d.a = Q; d.b = g.HP; d.c = IMG_DH1; d.e = IMG_H1;
                     Acc da; da.rd.push_back({R_TMEM, Q, Q + g.HP}); da.rd.push_back({R_IMG0 + IMG_H1, 0, g.HP});
                     da.wr.push_back({R_TMEM, Q, Q + g.HP}); da.wr.push_back({R_IMG0 + IMG_DH1, 0, g.HP});
                     b.push_epi(d, da);
@@ -472,7 +481,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             // dA = dH1 * W1
             b.gemm_ts(w1tg(net), {{Q, g.HP / 8}}, g.tm_da, true);
             {
-                T3Epi e{}; e.type = T3E_DA; e.a = (int16_t)g.tm_da; e.b = (int16_t)(g.KX + p.dc); e.c = (int16_t)tab_da;
+                T3Epi e{}; e.type = T3E_DA; e.a = g.tm_da; e.b = (g.KX + p.dc); e.c = tab_da;
                 Acc a; a.rd.push_back({R_TMEM, g.tm_da, g.tm_da + g.KX + p.dc});
                 b.push_epi(e, a);
             }
@@ -487,14 +496,14 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         e_in();
         fwd_chain(0, false, true);
         {
-            T3Epi e{}; e.type = T3E_OUTS; e.a = (int16_t)g.tm_out; e.b = (int16_t)g.OC;
+            T3Epi e{}; e.type = T3E_OUTS; e.a = g.tm_out; e.b = g.OC;
             Acc a; a.rd.push_back({R_TMEM, g.tm_out, g.tm_out + g.OC});
             b.push_epi(e, a);
         }
         // ---- phase 2: T forward, coupling, T backward ----
         fwd_chain(1, true, true);
         {
-            T3Epi e{}; e.type = T3E_CPL; e.a = (int16_t)g.tm_out; e.b = (int16_t)g.OC; e.c = (int16_t)tab_out; e.d = (int16_t)g.tm_dout; e.e = (int16_t)g.KD;
+            T3Epi e{}; e.type = T3E_CPL; e.a = g.tm_out; e.b = g.OC; e.c = tab_out; e.d = g.tm_dout; e.e = g.KD;
             e.off = g.part[1][3];
             Acc a; a.rd.push_back({R_TMEM, g.tm_out, g.tm_out + g.OC});
             a.wr.push_back({R_TMEM, g.tm_dout, g.tm_dout + g.KD}); a.wr.push_back({R_IMG0 + IMG_DOUT, 0, g.OC});
@@ -504,7 +513,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         // ---- phase 3: S forward again (activations), S backward ----
         fwd_chain(0, true, false);
         {
-            T3Epi e{}; e.type = T3E_DS; e.a = (int16_t)g.tm_dout; e.b = (int16_t)g.OC; e.e = (int16_t)g.KD; e.off = g.part[0][3];
+            T3Epi e{}; e.type = T3E_DS; e.a = g.tm_dout; e.b = g.OC; e.e = g.KD; e.off = g.part[0][3];
             Acc a; a.wr.push_back({R_TMEM, g.tm_dout, g.tm_dout + g.KD}); a.wr.push_back({R_IMG0 + IMG_DOUT, 0, g.OC});
             b.push_epi(e, a);
         }
@@ -512,7 +521,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
     }
     b.infer_waits();
     t.n_packed = (int64_t)t.pack_src.size();
-    if ((int)t.tab16.size() * 2 > 4096) return fail("internal: epilogue tables exceed their shared-memory reservation");
+    if ((int)t.tab16.size() * 2 > tab_bytes || (int)(t.epis.size() * sizeof(T3Epi)) > epi_bytes) return fail("internal: epilogue tables exceed their shared-memory reservation");
     for (const T3Chunk& c : t.chunks)
         if ((int)c.bytes > t.slot_bytes) return fail("internal: weight slab larger than a ring slot");
     if (t.epis.size() > 32000 || t.mmas.size() > 32000) return fail("program too long");

@@ -26,7 +26,7 @@
 
 namespace hint {
 
-constexpr int kT3EpiWarps = 8;
+constexpr int kT3EpiWarps = 16;                       // 4 warps per TMEM lane quadrant: 4 column slices of every wide step
 constexpr int kT3Threads = 32 * (kT3EpiWarps + 2);   // + issuer warp + loader warp
 constexpr int kT3NB = 16;                             // mbarriers per signal sequence
 constexpr int kT3MaxSlots = 4;
@@ -52,7 +52,7 @@ struct T3Mma {
 };
 
 // ---- epilogue program ------------------------------------------------------------------------------------------
-enum : uint8_t {
+enum : int32_t {
     T3E_IN = 0,      // subnet inputs of a group: state columns -> TMEM A columns + input image
     T3E_HID,         // hidden layer: relu + tf32 rounding in place (+ image, + ones block)
     T3E_OUTS,        // phase 1: s outputs -> state
@@ -62,19 +62,21 @@ enum : uint8_t {
     T3E_DA,          // input gradient: accumulate into the gradient state
     T3E_FLUSH,       // weight-gradient accumulator -> partial buffer
 };
+// all fields 32-bit: the kernel reads a step as three 128-bit loads and never unpacks sub-word fields (see the note at
+// T3MmaWords in tc3_kernels.cuh)
 struct T3Epi {
-    uint8_t type;
-    uint8_t flags;
-    int16_t wait_mma;    // MMA signal (index inside the tile program) that must have fired, -1 = none
+    int32_t type;
+    int32_t flags;
+    int32_t wait_mma;    // MMA signal (index inside the tile program) that must have fired, -1 = none
     int32_t off;         // partial-buffer offset (T3E_FLUSH, T3E_CPL, T3E_DS)
-    int16_t a, b, c, d, e, f, g, h;   // per type, see plan_tc3.cpp: the emitters in build_tc3_plan()
+    int32_t a, b, c, d, e, f, g, h;   // per type, see plan_tc3.cpp: the emitters in build_tc3_plan()
 };
 // T3E_HID flags
-enum : uint8_t { T3H_IMG = 1, T3H_ONES = 2, T3H_IMG_ONES = 4 };
+enum : int32_t { T3H_IMG = 1, T3H_ONES = 2, T3H_IMG_ONES = 4 };
 // T3E_DHID flags
-enum : uint8_t { T3D_MASK_TMEM = 1 };   // relu mask from TMEM (else from an image)
+enum : int32_t { T3D_MASK_TMEM = 1 };   // relu mask from TMEM (else from an image)
 // T3E_FLUSH kinds (field g): which column range of a lane's node is flushed
-enum : int16_t { T3F_W2 = 0, T3F_W1 = 1, T3F_W3 = 2 };
+enum : int32_t { T3F_W2 = 0, T3F_W1 = 1, T3F_W3 = 2 };
 
 struct T3Chunk {
     uint32_t g_off;      // float offset in the packed weight buffer
@@ -105,7 +107,7 @@ struct T3Plan {
     float alpha = 0.f;
     std::vector<T3Group> groups;          // root level first
     // shared memory map (bytes from the start of dynamic shared memory)
-    int sm_bars = 0, sm_tab16 = 0, sm_xs = 0, sm_gs = 0, sm_os = 0, sm_stage = 0, sm_red = 0, sm_ring = 0;
+    int sm_bars = 0, sm_tab16 = 0, sm_epis = 0, sm_xs = 0, sm_gs = 0, sm_os = 0, sm_stage = 0, sm_red = 0, sm_ring = 0;
     int sm_img[kT3Imgs] = {0, 0, 0, 0, 0};
     int img_rows[kT3Imgs] = {0, 0, 0, 0, 0};   // allocated rows (multiple of 8); slab = rows * 128 bytes per 32 samples
     int n_imgs_hidden = 2;                       // 2 or 3 hidden image buffers
@@ -123,6 +125,7 @@ struct T3Plan {
     std::vector<int32_t> pack_src;       // packed[i] = pack_src[i] < 0 ? 0 : tf32(params[pack_src[i]])
     int64_t n_partial = 0;               // floats per CTA
     std::vector<int32_t> unpack_src;     // dparams[i] = sum over CTAs of partial[unpack_src[i]]
+    std::vector<uint8_t> unpack_q4;      // 1: the parameter (a layer-3 bias) is the sum of 4 per-quadrant slots at stride 32
     // model of one tile, for reports: MMA instructions and tensor-pipe cycles (N/2 per instruction)
     int64_t n_mma_instr = 0, tensor_cycles = 0;
 };

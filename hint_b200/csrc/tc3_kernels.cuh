@@ -2,12 +2,13 @@
 // over it) in TF32.  Executes the programs of plan_tc3.h; the machine model is described there.
 //
 // Warp roles (320 threads, one CTA per SM, persistent over tiles of 128 samples):
-//   warps 0-7  epilogue.  Thread = one sample (TMEM lane = tid & 127); the two warpgroups split the columns of the wide
-//              steps (hidden layers, flushes); the narrow, state-touching steps run on warpgroup 0 only, so the per-sample
-//              state in shared memory is private to one thread and needs no barrier.
-//   warp 8     MMA issuer (one elected thread).  All MMA operands derive from the kernel-parameter bank (program passed
+//   warps 0-15 epilogue.  Thread = one sample (TMEM lane = tid & 127); the four warpgroups split the columns of the wide
+//              steps (hidden layers, flushes) - with 2 warps per scheduler the epilogues were issue-latency bound; the
+//              narrow, state-touching steps run on warpgroup 0 only, so the per-sample state in shared memory is private to
+//              one thread and needs no barrier.
+//   warp 16    MMA issuer (one elected thread).  All MMA operands derive from the kernel-parameter bank (program passed
 //              by value) and uniform arithmetic, so tcgen05.mma issues without the compiler's divergence loop.
-//   warp 9     loader: weight slabs -> shared-memory ring (cp.async.bulk, mbarrier complete_tx).
+//   warp 17    loader: weight slabs -> shared-memory ring (cp.async.bulk, mbarrier complete_tx).
 // Synchronisation: two monotone signal sequences on mbarrier rings (MMA groups committed, epilogue steps finished) with
 // the wait indices the planner inferred; full/empty barriers per ring slot.
 #pragma once
@@ -18,10 +19,24 @@ namespace hint {
 
 constexpr int kT3MaxMma = 1200;
 
+// One issuer record as five 32-bit words in the kernel-parameter bank.  Sub-word fields are decoded with shifts, never with
+// 16-bit struct members: ptxas 12.9 miscompiled `mov.b32 {%rs, %rs}` unpacks of dynamically indexed ld.param words (the
+// consumer read a register the load never wrote), which made the issuer skip its waits.
+//   w0 idesc | w1 b_off | w2 d_col | a_col << 16 | w3 nk | b_sbo16 << 16 | w4 flags | wait_epi << 16
+struct T3MmaWords { uint32_t w[5]; };
+inline T3MmaWords t3_pack_mma(const T3Mma& m) {
+    T3MmaWords r;
+    r.w[0] = m.idesc; r.w[1] = m.b_off;
+    r.w[2] = (uint32_t)m.d_col | ((uint32_t)m.a_col << 16);
+    r.w[3] = (uint32_t)m.nk | ((uint32_t)m.b_sbo16 << 16);
+    r.w[4] = (uint32_t)m.flags | ((uint32_t)(uint16_t)m.wait_epi << 16);
+    return r;
+}
+
 struct T3Prog {
     int n_mma, n_epi, n_chunks, n_signals;
     int n_slots, slot_bytes;
-    int sm_bars, sm_tab16, sm_xs, sm_gs, sm_os, sm_red, sm_ring;
+    int sm_bars, sm_tab16, sm_epis, sm_xs, sm_gs, sm_os, sm_red, sm_ring;
     int sm_img[kT3Imgs];
     int img_rows[kT3Imgs];
     int xp, op, d, dc, n_tab16;
@@ -29,7 +44,7 @@ struct T3Prog {
     const T3Epi* epis;
     const T3Chunk* chunks;
     const int16_t* tab16;
-    T3Mma mmas[kT3MaxMma];
+    T3MmaWords mmas[kT3MaxMma];
 };
 
 // barrier slots (uint64_t) at sm_bars
@@ -70,7 +85,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ z, const float* __restrict__ c,
                     const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ dlogdet,
                     float* __restrict__ x_rec, float* __restrict__ dx, float* __restrict__ dcond, float* __restrict__ partials,
-                    long long n_partial, long long B, float* dbg) {
+                    long long n_partial, long long B, float* dbg, long long* prof) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P.sm_bars);
@@ -78,6 +93,11 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int16_t* s_tab = reinterpret_cast<int16_t*>(smem + P.sm_tab16);
     for (int i = tid; i < P.n_tab16; i += kT3Threads) s_tab[i] = P.tab16[i];
+    {   // the epilogue program lives in shared memory: a global fetch per step was ~700 cycles of exposed L2 latency
+        int4* s_epis4 = reinterpret_cast<int4*>(smem + P.sm_epis);
+        const int4* g4 = reinterpret_cast<const int4*>(P.epis);
+        for (int i = tid; i < P.n_epi * 3; i += kT3Threads) s_epis4[i] = g4[i];
+    }
     if (tid == 0) {
         for (int i = 0; i < kT3MaxSlots; ++i) { mbar_init(bars + T3B_FULL + i, 1); mbar_init(bars + T3B_EMPTY + i, 1); }
         for (int i = 0; i < kT3NB; ++i) { mbar_init(bars + T3B_MMA + i, 1); mbar_init(bars + T3B_EPI + i, kT3EpiWarps); }
@@ -115,46 +135,52 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
             uint32_t nslot = 0, nph = 0, cur = 0;
             uint32_t msig = 0;        // MMA signals committed so far (all tiles)
             uint32_t ebase = 0;       // epilogue steps of the previous tiles
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int tile_iter = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
                 int waited = -1;
+                const bool pt = blockIdx.x == 0 && tile_iter == 1;   // developer timeline of CTA 0's second tile
                 for (int i = 0; i < P.n_mma; ++i) {
-                    const T3Mma m = P.mmas[i];
-                    if ((int)m.wait_epi > waited) {
-                        const uint32_t g = ebase + (uint32_t)m.wait_epi;
+                    const uint32_t w0 = P.mmas[i].w[0], w1 = P.mmas[i].w[1], w2 = P.mmas[i].w[2], w3 = P.mmas[i].w[3], w4 = P.mmas[i].w[4];
+                    const uint32_t m_idesc = w0, m_boff = w1, m_dcol = w2 & 0xFFFFu, m_acol = w2 >> 16, m_nk = w3 & 0xFFFFu, m_sbo16 = w3 >> 16;
+                    const uint32_t m_flags = w4 & 0xFFFFu;
+                    const int m_wait = (int)w4 >> 16;   // arithmetic shift: sign-extended 16-bit field
+                    if (m_wait > waited) {
+                        const uint32_t g = ebase + (uint32_t)m_wait;
                         mbar_wait(bars + T3B_EPI + (g % kT3NB), (g / kT3NB) & 1);
                         fence_after_sync();
-                        waited = m.wait_epi;
+                        waited = m_wait;
                     }
-                    uint32_t acc = (m.flags & T3M_ZERO) ? 0u : 1u;
-                    if (!(m.flags & T3M_SS)) {
-                        if (m.flags & T3M_NEWCHUNK) {
+                    if (prof && pt && i < 1024) prof[i] = clock64();
+                    uint32_t acc = (m_flags & T3M_ZERO) ? 0u : 1u;
+                    if (!(m_flags & T3M_SS)) {
+                        if (m_flags & T3M_NEWCHUNK) {
                             cur = nslot;
                             mbar_wait(bars + T3B_FULL + cur, nph);
                             if (++nslot == (uint32_t)P.n_slots) { nslot = 0; nph ^= 1; }
                         }
-                        uint32_t b_lo = ((ring16 + cur * slot16 + (m.b_off >> 4)) & 0x3FFFu) | (8u << 16);   // LBO = 128 B
-                        const uint32_t b_hi = (uint32_t)m.b_sbo16 | (1u << 14);                               // SBO, descriptor version 1
-                        uint32_t a_t = m.a_col;
-                        for (int ks = 0; ks < (int)m.nk; ++ks) {
-                            mma_ts(m.d_col, a_t, ((uint64_t)b_hi << 32) | b_lo, m.idesc, acc);
+                        uint32_t b_lo = ((ring16 + cur * slot16 + (m_boff >> 4)) & 0x3FFFu) | (8u << 16);   // LBO = 128 B
+                        const uint32_t b_hi = m_sbo16 | (1u << 14);                                            // SBO, descriptor version 1
+                        uint32_t a_t = m_acol;
+                        for (uint32_t ks = 0; ks < m_nk; ++ks) {
+                            mma_ts(m_dcol, a_t, ((uint64_t)b_hi << 32) | b_lo, m_idesc, acc);
                             b_lo += 16;   // two core matrices (256 B) along K
                             a_t += 8;
                             acc = 1u;
                         }
-                        if (m.flags & T3M_ENDCHUNK) commit(bars + T3B_EMPTY + cur);
+                        if (m_flags & T3M_ENDCHUNK) commit(bars + T3B_EMPTY + cur);
                     } else {
-                        const int ai = (int)(m.b_off & 0xFF), bi = (int)((m.b_off >> 8) & 0xFF);
-                        const uint32_t abase = sbase + (uint32_t)P.sm_img[ai] + (uint32_t)m.a_col * 1024u;
+                        const int ai = (int)(m_boff & 0xFF), bi = (int)((m_boff >> 8) & 0xFF);
+                        const uint32_t abase = sbase + (uint32_t)P.sm_img[ai] + m_acol * 1024u;
                         const uint32_t bbase = sbase + (uint32_t)P.sm_img[bi];
                         const uint32_t aslab = (uint32_t)P.img_rows[ai] * 128u, bslab = (uint32_t)P.img_rows[bi] * 128u;
                         for (int kk = 0; kk < 16; ++kk) {
                             const uint32_t o = (uint32_t)(kk & 3) * 32u;
-                            mma_ss(m.d_col, t3_desc_sw128(abase + (uint32_t)(kk >> 2) * aslab + o),
-                                   t3_desc_sw128(bbase + (uint32_t)(kk >> 2) * bslab + o), m.idesc, acc);
+                            mma_ss(m_dcol, t3_desc_sw128(abase + (uint32_t)(kk >> 2) * aslab + o),
+                                   t3_desc_sw128(bbase + (uint32_t)(kk >> 2) * bslab + o), m_idesc, acc);
                             acc = 1u;
                         }
                     }
-                    if (m.flags & T3M_COMMIT) { commit(bars + T3B_MMA + (msig % kT3NB)); ++msig; }
+                    if (m_flags & T3M_COMMIT) { commit(bars + T3B_MMA + (msig % kT3NB)); ++msig; }
                 }
                 ebase += (uint32_t)P.n_epi;
                 if (dbg) commit(bars + T3B_DONE);   // developer dump (tests/cuda/dbg_tc3.py): everything issued has completed
@@ -162,7 +188,8 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
         }
     } else {
         // ================= epilogue warps =================
-        const int wg = tid >> 7;            // warpgroup 0 / 1
+        const int wg = tid >> 7;            // warpgroup 0 .. 3: column slice of the wide steps
+        constexpr int kWG = kT3EpiWarps / 4;
         const int row = tid & 127;          // sample within the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         float* XS = reinterpret_cast<float*>(smem + P.sm_xs) + row * P.xp;
@@ -210,12 +237,20 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
             named_bar_sync(1, 32 * kT3EpiWarps);
             int waited = -1;
             for (int si = 0; si < P.n_epi; ++si, ++estep) {
-                const T3Epi e = P.epis[si];
+                T3Epi e;
+                {
+                    const int4* ep = reinterpret_cast<const int4*>(smem + P.sm_epis) + 3 * si;
+                    const int4 e0 = ep[0], e1 = ep[1], e2 = ep[2];
+                    e.type = e0.x; e.flags = e0.y; e.wait_mma = e0.z; e.off = e0.w;
+                    e.a = e1.x; e.b = e1.y; e.c = e1.z; e.d = e1.w; e.e = e2.x; e.f = e2.y; e.g = e2.z; e.h = e2.w;
+                }
                 if ((int)e.wait_mma > waited) {
                     const uint32_t g = sbase_sig + (uint32_t)e.wait_mma;
                     mbar_wait(bars + T3B_MMA + (g % kT3NB), (g / kT3NB) & 1);
                     waited = e.wait_mma;
                 }
+                long long t_wait_done = 0;
+                if (prof) t_wait_done = clock64();
                 fence_after_sync();
                 switch (e.type) {
                     case T3E_IN: {
@@ -231,26 +266,25 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                 }
                                 st8(lane_base + (uint32_t)(e.c + c0), v);
                             }
-                            wait_st();
                         }
                         break;
                     }
                     case T3E_HID: {
                         const int ncols = e.b;
-                        const int half = ((ncols >> 1) + 15) & ~15;
-                        const int q0 = wg ? half : 0, q1 = wg ? ncols : half;
+                        const int slice = ((ncols + kWG - 1) / kWG + 15) & ~15;
+                        const int q0 = min(wg * slice, ncols), q1 = min(q0 + slice, ncols);
                         const uint32_t a0 = lane_base + (uint32_t)e.a;
                         unsigned char* im = img_ptr(e.c);
                         const bool to_img = (e.flags & T3H_IMG) != 0;
-                        for (int q = q0; q < q1; q += 64) {
-                            float v[4][16];
+                        for (int q = q0; q < q1; q += 32) {
+                            float v[2][16];
                             const int nb = (q1 - q) >> 4;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
+                            for (int u = 0; u < 2; ++u)
                                 if (u < nb) ld16(a0 + q + 16 * u, v[u]);
                             wait_ld();
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
+                            for (int u = 0; u < 2; ++u) {
                                 if (u < nb) {
 #pragma unroll
                                     for (int j = 0; j < 16; ++j) v[u][j] = t3_round(fmaxf(v[u][j], 0.f));
@@ -263,7 +297,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                 }
                             }
                         }
-                        if (wg == 1 && (e.flags & T3H_ONES)) {
+                        if (wg == kWG - 1 && (e.flags & T3H_ONES)) {
                             float o[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                             st8(a0 + ncols, o);
                             if (e.flags & T3H_IMG_ONES) {
@@ -272,7 +306,6 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                 for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(ib + xo[j]) = o[j];
                             }
                         }
-                        wait_st();
                         break;
                     }
                     case T3E_OUTS: {
@@ -294,8 +327,9 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                             const int oc = e.b, kd = e.e;
                             const int tm_dout = cpl ? e.d : e.a;
                             unsigned char* im4 = img_ptr(4);
+                            float* pq = my_part + e.off + (warp & 3) * 32;   // this quadrant's bias-gradient slots
                             for (int c0 = 0; c0 < kd; c0 += 8) {
-                                float tv[8], o[8];
+                                float tv[8], o[8], bs[8];
                                 if (cpl) { ld8(lane_base + (uint32_t)(e.a + c0), tv); wait_ld(); }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
@@ -316,32 +350,51 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                         } else {
                                             dout = OS[col];
                                         }
-                                        // bias gradient of layer 3: column sum over the tile's samples
-                                        float sred = dout;
-#pragma unroll
-                                        for (int sh = 16; sh > 0; sh >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, sh);
-                                        if (lane == 0) s_red[(warp & 3) * 32 + col] = sred;
                                         *reinterpret_cast<float*>(im4 + (uint32_t)(c0 >> 3) * 1024u + xo[j]) = t3_round(dout);
                                     }
+                                    bs[j] = dout;
                                     o[j] = t3_round(dout);
                                 }
                                 st8(lane_base + (uint32_t)(tm_dout + c0), o);
+                                // bias gradient of layer 3: the 8 column sums over this quadrant's 32 samples as a reduce-scatter
+                                // butterfly (9 shuffles instead of 40): afterwards lane 4*k holds the sum of column k
+                                {
+                                    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
+                                    float a4[4], a2[2], a1;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float send = hi16 ? bs[k] : bs[k + 4];
+                                        const float keep = hi16 ? bs[k + 4] : bs[k];
+                                        a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        const float send = hi8 ? a4[k] : a4[k + 2];
+                                        const float keep = hi8 ? a4[k + 2] : a4[k];
+                                        a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                                    }
+                                    {
+                                        const float send = hi4 ? a2[0] : a2[1];
+                                        const float keep = hi4 ? a2[1] : a2[0];
+                                        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                                    }
+                                    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+                                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                                    // lane bits (16, 8, 4) select the column: col = 4*bit16 + 2*bit8 + bit4
+                                    const int kcol = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                                    if ((lane & 3) == 0 && c0 + kcol < oc) {
+                                        float* p1 = pq + c0 + kcol;
+                                        if (first_tile) *p1 = a1; else atomicAdd(p1, a1);   // private slot: plain accumulation, issued as RED (no round trip)
+                                    }
+                                }
                             }
-                            wait_st();
-                            named_bar_sync(2, 128);
-                            if (tid < oc) {
-                                const float sum = (s_red[tid] + s_red[32 + tid]) + (s_red[64 + tid] + s_red[96 + tid]);
-                                float* pp = my_part + e.off + tid;
-                                *pp = first_tile ? sum : *pp + sum;
-                            }
-                            named_bar_sync(2, 128);   // s_red is reused by the next coupling step
                         }
                         break;
                     }
                     case T3E_DHID: {
                         const int ncols = e.b;
-                        const int half = ((ncols >> 1) + 15) & ~15;
-                        const int q0 = wg ? half : 0, q1 = wg ? ncols : half;
+                        const int slice = ((ncols + kWG - 1) / kWG + 15) & ~15;
+                        const int q0 = min(wg * slice, ncols), q1 = min(q0 + slice, ncols);
                         const uint32_t a0 = lane_base + (uint32_t)e.a;
                         unsigned char* imo = img_ptr(e.c);
                         const bool mask_tmem = (e.flags & T3D_MASK_TMEM) != 0;
@@ -375,7 +428,6 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                 }
                             }
                         }
-                        wait_st();
                         break;
                     }
                     case T3E_DA: {
@@ -409,7 +461,11 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         const int x0 = e.c, x1 = e.g == T3F_W2 ? e.c + 1 : e.g == T3F_W1 ? e.c + dc + 1 : e.c;
                         float* pp = my_part + e.off + row;
                         const int ncols = e.b;
-                        for (int q = 16 * wg; q < ncols; q += 32) {
+                        // accumulate into the CTA's private, L2-resident partial buffer.  Every address is owned by one thread and
+                        // tiles are sequential, so a reduction without return value (RED: no L2 round trip on the critical path)
+                        // is still a deterministic, uncontended accumulation; the first tile stores.
+                        auto in_range = [&](int col) { return (col >= c0 && col < c1) || (x0 >= 0 && col >= x0 && col < x1); };
+                        for (int q = 16 * wg; q < ncols; q += 16 * kWG) {
                             float v[16];
                             ld16(lane_base + (uint32_t)(e.a + q), v);
                             wait_ld();
@@ -417,9 +473,9 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
                                     const int col = q + j;
-                                    if ((col >= c0 && col < c1) || (x0 >= 0 && col >= x0 && col < x1)) {
+                                    if (in_range(col)) {
                                         float* p1 = pp + (size_t)col * 128;
-                                        *p1 = first_tile ? v[j] : *p1 + v[j];
+                                        if (first_tile) __stcg(p1, v[j]); else atomicAdd(p1, v[j]);
                                     }
                                 }
                             }
@@ -429,9 +485,18 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                     default: break;
                 }
                 // publish: TMEM / image writes of this step are visible to the tensor core before the signal fires
+                long long ts0 = 0, ts1 = 0, ts2 = 0;
+                if (prof) ts0 = clock64();
+                wait_st();
+                if (prof) ts1 = clock64();
                 fence_proxy_async_smem();
+                if (prof) ts2 = clock64();
                 fence_before_sync();
                 __syncwarp();
+                if (prof && blockIdx.x == 0 && !first_tile && estep < 2u * (uint32_t)P.n_epi && si < 512 && lane == 0 && (warp == 0 || warp == 4)) {   // warpgroups 0 and 1
+                    prof[1024 + 2 * si + (warp >> 2)] = clock64();
+                    if (warp == 0) { prof[2048 + si] = t_wait_done; prof[2560 + 3 * si] = ts0; prof[2561 + 3 * si] = ts1; prof[2562 + 3 * si] = ts2; }
+                }
                 if (lane == 0) mbar_arrive(bars + T3B_EPI + (estep % kT3NB));
             }
             sbase_sig += (uint32_t)P.n_signals;
@@ -439,7 +504,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                 mbar_wait(bars + T3B_DONE, 0);
                 fence_after_sync();
                 named_bar_sync(1, 32 * kT3EpiWarps);
-                for (int q = 256 * wg; q < 256 * wg + 256; q += 16) {
+                for (int q = (512 / kWG) * wg; q < (512 / kWG) * (wg + 1); q += 16) {
                     float v[16];
                     ld16(lane_base + (uint32_t)q, v);
                     wait_ld();
@@ -489,6 +554,14 @@ __global__ void hint_tc3_reduce_kernel(const int* __restrict__ dst, const float*
         if (t < 0) continue;
         const float* p = partials + i;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (t & (1 << 30)) {   // layer-3 bias: four per-quadrant slots at stride 32
+            for (int q = 0; q < nctas; ++q) {
+                const float* pq = p + (long long)q * n_partial;
+                a0 += pq[0]; a1 += pq[32]; a2 += pq[64]; a3 += pq[96];
+            }
+            dparams[t & ~(1 << 30)] = (a0 + a1) + (a2 + a3);
+            continue;
+        }
         int q = 0;
         for (; q + 3 < nctas; q += 4) {
             a0 += p[(long long)q * n_partial];

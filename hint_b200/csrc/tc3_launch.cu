@@ -29,18 +29,18 @@ cudaError_t tc3_setup(const T3Plan& t, int num_sms, DevTc3& d) {
     if ((e = upload(&d.tab16, t.tab16)) != cudaSuccess) return e;
     if ((e = upload(&d.pack_src, t.pack_src)) != cudaSuccess) return e;
     std::vector<int32_t> dst((size_t)t.n_partial, -1);
-    for (size_t i = 0; i < t.unpack_src.size(); ++i) dst[(size_t)t.unpack_src[i]] = (int32_t)i;
+    for (size_t i = 0; i < t.unpack_src.size(); ++i) dst[(size_t)t.unpack_src[i]] = (int32_t)i | (t.unpack_q4[i] ? (1 << 30) : 0);
     if ((e = upload(&d.part_dst, dst)) != cudaSuccess) return e;
     T3Prog* P = new T3Prog();
     std::memset(P, 0, sizeof(T3Prog));
     P->n_mma = (int)t.mmas.size(); P->n_epi = (int)t.epis.size(); P->n_chunks = (int)t.chunks.size(); P->n_signals = t.n_mma_signals;
     P->n_slots = t.n_slots; P->slot_bytes = t.slot_bytes;
-    P->sm_bars = t.sm_bars; P->sm_tab16 = t.sm_tab16; P->sm_xs = t.sm_xs; P->sm_gs = t.sm_gs; P->sm_os = t.sm_os; P->sm_red = t.sm_red; P->sm_ring = t.sm_ring;
+    P->sm_bars = t.sm_bars; P->sm_tab16 = t.sm_tab16; P->sm_epis = t.sm_epis; P->sm_xs = t.sm_xs; P->sm_gs = t.sm_gs; P->sm_os = t.sm_os; P->sm_red = t.sm_red; P->sm_ring = t.sm_ring;
     for (int i = 0; i < kT3Imgs; ++i) { P->sm_img[i] = t.sm_img[i]; P->img_rows[i] = t.img_rows[i]; }
     P->xp = t.xp; P->op = t.op; P->d = t.d; P->dc = t.dc; P->n_tab16 = (int)t.tab16.size();
     P->alpha = t.alpha;
     P->epis = d.epis; P->chunks = d.chunks; P->tab16 = d.tab16;
-    std::copy(t.mmas.begin(), t.mmas.end(), P->mmas);
+    for (size_t i = 0; i < t.mmas.size(); ++i) P->mmas[i] = t3_pack_mma(t.mmas[i]);
     d.prog = P;
     d.num_sms = num_sms;
     return cudaFuncSetAttribute((const void*)hint_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem_bytes);
@@ -65,9 +65,9 @@ int tc3_bwd_ctas(const DevTc3& d, long long B) {
 
 cudaError_t tc3_launch_bwd(const T3Plan& t, const DevTc3& d, int grid, const float* z, const float* cond, const float* packed,
                            const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc, float* partials,
-                           float* dparams, long long B, cudaStream_t st) {
+                           float* dparams, long long B, cudaStream_t st, long long* prof) {
     hint_tc3_bwd_kernel<<<grid, kT3Threads, t.smem_bytes, st>>>(*d.prog, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
-                                                                (long long)t.n_partial, B, nullptr);
+                                                                (long long)t.n_partial, B, nullptr, prof);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int threads = 256;
@@ -92,7 +92,7 @@ cudaError_t tc3_debug_run(const T3Plan& t, const DevTc3& d, int n_epi_limit, con
     while (nm < (int)t.mmas.size() && nm > 0 && !(t.mmas[nm - 1].flags & T3M_SS) && !(t.mmas[nm - 1].flags & T3M_ENDCHUNK)) ++nm;
     P.n_mma = nm; P.n_epi = n_epi_limit; P.n_chunks = nch;
     hint_tc3_bwd_kernel<<<1, kT3Threads, t.smem_bytes, st>>>(P, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
-                                                             (long long)t.n_partial, std::min<long long>(B, 128), dump);
+                                                             (long long)t.n_partial, std::min<long long>(B, 128), dump, nullptr);
     return cudaGetLastError();
 }
 

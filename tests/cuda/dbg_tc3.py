@@ -29,12 +29,19 @@ def main():
         if craft == 'bias': flat[35:40] = torch.tensor([10., 20., 30., 40., 50.])
         if craft == 'both': flat[10:35] = torch.eye(5).flatten(); flat[35:40] = torch.tensor([10., 20., 30., 40., 50.])
         if craft == 'full': flat[10:35] = torch.arange(25.).float() + 1
+        rnd = (0.3 * torch.randn(92, generator=torch.Generator().manual_seed(11))).float()
+        if craft in ('r1', 'r12'): flat[0:10] = rnd[0:10]
+        if craft == 'r1': flat[10:35] = torch.eye(5).flatten(); flat[35:40] = torch.tensor([10., 20., 30., 40., 50.])
+        if craft in ('r2', 'r12'): flat[10:40] = rnd[10:40]
+        if craft == 'r1p': flat[0:5] = rnd[0:5].abs() * 0.1; flat[10:35] = torch.eye(5).flatten()
+        if craft == 'r2i': flat[10:35] = torch.round(rnd[10:35] * 20)
+        if craft == 'r2h': flat[10:35] = torch.round(rnd[10:35] * 20) / 1024
     z = torch.randn(B, d, generator=g); dz = torch.randn(B, d, generator=g) / B; dJ = torch.randn(B, generator=g) / B
     lib = _lib.load()
     lib.hint_dev_tc3_debug.restype = ctypes.c_int
     nbytes = lib.hint_workspace_bytes(tp._h, B, _lib.WS_BACKWARD)
     ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    dump = torch.zeros(65536 + 60000, dtype=torch.float32, device=dev)
+    dump = torch.zeros(131072 + 4096, dtype=torch.float32, device=dev)
     zg, dzg, dJg, fg = z.to(dev), dz.to(dev), dJ.to(dev), flat.to(dev)
     xrec = torch.zeros(B, d, device=dev); dx = torch.zeros(B, d, device=dev)
     layout = (ctypes.c_int32 * 32)()
@@ -76,9 +83,13 @@ def main():
                 errs[f"img{i}"] = cmp(sm_g[sm_img[i] // 4: sm_img[i] // 4 + rows[i] * 128], img_e[o:o + rows[i] * 128], "img")
             o += rows[i] * 128
         worst = max(errs.values())
+        if os.environ.get('TIMES') and n <= 4:
+            ts = dump[131072:].cpu().numpy().view(np.int64)
+            t0 = ts[ts > 0].min()
+            print('  issue clocks (after wait) of records:', (ts[:6] - t0).tolist()); print('  arrive clocks of epi steps x warps:', [(ts[64 + 8 * s: 64 + 8 * s + 8] - t0).tolist() for s in range(min(n, 4))])
         if craft and n in (2, 3, 4):
             np.set_printoptions(precision=3, suppress=True, linewidth=200)
-            print('gpu Q lane0', tm_g[0, 24:40]); print('emu Q lane0', tm_e[0, 24:40]); print('gpu P lane0', tm_g[0, 0:24]); print('gpu OUT lane0', tm_g[0, 96:100], 'emu', tm_e[0, 96:100])
+            print('gpu Q lane0', tm_g[0, 24:32], 'lane5', tm_g[5, 24:32]); print('emu Q lane0', tm_e[0, 24:32], 'lane5', tm_e[5, 24:32]); print('gpu P lane0', tm_g[0, 0:24]); print('gpu OUT lane0', tm_g[0, 96:100], 'emu', tm_e[0, 96:100])
         bad_cols = ""
         if errs["tmem"] > 1e-2:
             m = np.isfinite(tm_e)

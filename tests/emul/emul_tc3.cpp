@@ -174,8 +174,8 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                             OS[(size_t)s * op + col] = ds;
                             tm(s, e.d + col) = rt(dzl); im(4, col, s) = rt(dzl);
                             bsum += dzl;
+                            if ((s & 31) == 31) { part[(size_t)e.off + 32 * (s >> 5) + col] += bsum; bsum = 0; }
                         }
-                        part[(size_t)e.off + col] += bsum;
                     }
                     for (int s = 0; s < 128; ++s) for (int col = e.b; col < e.e; ++col) tm(s, e.d + col) = 0.f;
                     break;
@@ -186,8 +186,8 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                             const float ds = OS[(size_t)s * op + col];
                             tm(s, e.a + col) = rt(ds); im(4, col, s) = rt(ds);
                             bsum += ds;
+                            if ((s & 31) == 31) { part[(size_t)e.off + 32 * (s >> 5) + col] += bsum; bsum = 0; }
                         }
-                        part[(size_t)e.off + col] += bsum;
                     }
                     for (int s = 0; s < 128; ++s) for (int col = e.b; col < e.e; ++col) tm(s, e.a + col) = 0.f;
                     break;
@@ -259,7 +259,11 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
             for (int j = 0; j < p.dc; ++j) dcond[(row0 + s) * p.dc + j] = GS[(size_t)s * xp + p.d + j];
         }
     }
-    for (long long i = 0; i < p.n_params; ++i) dparams[i] = (float)part[(size_t)t.unpack_src[i]];
+    for (long long i = 0; i < p.n_params; ++i) {
+        double v = part[(size_t)t.unpack_src[i]];
+        if (t.unpack_q4[(size_t)i]) for (int q = 1; q < 4; ++q) v += part[(size_t)t.unpack_src[i] + 32 * q];
+        dparams[i] = (float)v;
+    }
     if (tmem_out) {
         memcpy(tmem_out, T.data(), T.size() * 4);
         size_t o = 0;
