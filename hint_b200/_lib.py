@@ -40,12 +40,23 @@ def load():
     try:
         from . import build as _build
         if not override and _build.is_stale():
-            _build.build()
+            # one builder at a time: under torchrun every rank imports at once, and concurrent nvcc runs would write the same
+            # object files / shared library (a rank could dlopen a half-written .so)
+            import fcntl
+            with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    if _build.is_stale():
+                        _build.build()
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
     except Exception as e:  # no nvcc on this machine: fall through and require the prebuilt .so
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"hint_b200: native library {LIB_PATH} is missing and could not be built ({e}). "
                 "Run `python -m hint_b200.build` (needs nvcc, sm_100a). There is no fallback path.") from e
+        import warnings
+        warnings.warn(f"hint_b200: rebuilding the native library failed ({e}); loading the existing, possibly stale {LIB_PATH}")
     lib = ctypes.CDLL(override or LIB_PATH)
     vp, i32, i64, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
     lib.hint_plan_create.restype = ctypes.c_int

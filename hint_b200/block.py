@@ -112,6 +112,16 @@ class TreePlan:
         if shape is not None and tuple(t.shape) != tuple(shape):
             raise ValueError(f"hint_b200: {name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
 
+    @staticmethod
+    def _dense16(t):
+        """Contiguous and 16-byte aligned (the C ABI's contract).  `.contiguous()` is a no-op for a row slice like x[1:], whose
+        storage offset can leave the base pointer misaligned when d*4 is not a multiple of 16 - the reference accepts any tensor,
+        so such views are copied here instead of being rejected by the library."""
+        if t is None:
+            return None
+        t = t.contiguous()
+        return t.clone() if t.data_ptr() % 16 else t
+
     def forward(self, x, c, flat, rev=False, mode=None):
         """z, logdet = f(x; c) (rev=False) or f^-1(x; c) (rev=True).  hint.py:62-101."""
         B = x.shape[0]
@@ -121,9 +131,9 @@ class TreePlan:
             if c is None:
                 raise ValueError("hint_b200: block was built with dims_c but no condition was passed")
             self._check(c, "c", (B, self.dc))
-            c = c.contiguous()
-        x = x.contiguous()
-        flat = flat.contiguous()
+            c = self._dense16(c)
+        x = self._dense16(x)
+        flat = self._dense16(flat)
         with torch.cuda.device(x.device):
             z = torch.empty_like(x)
             J = torch.empty(B, dtype=torch.float32, device=x.device)
@@ -143,8 +153,8 @@ class TreePlan:
         self._check(flat, "params", (self.n_params,))
         if self.dc:
             self._check(c, "c", (B, self.dc))
-            c = c.contiguous()
-        z, dz, dJ, flat = z.contiguous(), dz.contiguous(), dJ.contiguous(), flat.contiguous()
+            c = self._dense16(c)
+        z, dz, dJ, flat = self._dense16(z), self._dense16(dz), self._dense16(dJ), self._dense16(flat)
         with torch.cuda.device(z.device):
             dx = torch.empty_like(z)
             dc = torch.empty(B, self.dc, dtype=torch.float32, device=z.device) if (self.dc and want_dc) else None
@@ -167,8 +177,9 @@ class _CouplingFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, c, flat, plan, rev):
-        z, J = plan.forward(x, c, flat, rev)
-        ctx.plan, ctx.rev = plan, rev
+        mode = _mode   # the precision mode is fixed per call: backward uses the kernels of the mode the forward ran in
+        z, J = plan.forward(x, c, flat, rev, mode=mode)
+        ctx.plan, ctx.rev, ctx.mode = plan, rev, mode
         ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat)
         return z, J
 
@@ -182,7 +193,7 @@ class _CouplingFn(torch.autograd.Function):
             dz = torch.zeros_like(z)
         if dJ is None:
             dJ = torch.zeros(z.shape[0], dtype=z.dtype, device=z.device)
-        dx, dc, dflat, _ = plan.backward(z, c if plan.dc else None, flat, dz, dJ, want_dc=ctx.needs_input_grad[1])
+        dx, dc, dflat, _ = plan.backward(z, c if plan.dc else None, flat, dz, dJ, mode=ctx.mode, want_dc=ctx.needs_input_grad[1])
         return (dx if ctx.needs_input_grad[0] else None, dc if ctx.needs_input_grad[1] else None,
                 dflat if ctx.needs_input_grad[2] else None, None, None)
 

@@ -83,12 +83,14 @@ def build(force=False, verbose=False):
         failed |= res.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libhint_b200.so")
-    cmd = [nvcc, "-shared", "-o", LIB] + [_obj(u) for u in UNITS]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp] + [_obj(u) for u in UNITS]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("linking libhint_b200.so failed")
+    os.replace(tmp, LIB)   # atomic: a concurrent importer never maps a half-written library
     return LIB
 
 
