@@ -5,9 +5,12 @@
 
 One "step" = one full training step of the workload's model on one batch of synthetic data:
 x += 0.01*randn -> forward (all blocks) -> NLL loss -> backward -> [NCCL grad all-reduce] -> clamp +-5 -> Adam
-(train_unconditional.py:121-144,174-176).  `value` = samples/s of that step with the batch resident in HBM;
-`e2e` = the same through host buffers (pinned H2D of the batch and D2H of the loss inside the timed region);
-forward+logdet and inverse throughputs are reported under "extra".  Default workload: the d=43 `hint_8` model of
+(train_unconditional.py:121-144,174-176), run through hint_b200.FusedTrainStep: every kernel of the step is this library's
+(`gpu_launches` is counted by the library).  `value` = samples/s of that step with the batch resident in HBM;
+`e2e` = the same through host buffers (pinned H2D of the batch and D2H of the loss inside the timed region, the copy
+prefetched one step ahead on a copy stream); forward+logdet and inverse throughputs are under "extra" and, as fractions of the
+TF32 peak MEASURED in the same run, under roofline.phases; "modes" repeats the step in fp32 / 3xTF32 and "configs" runs every
+BASELINE workload at its stated batch (1 GPU).  Default workload: the d=43 `hint_8` model of
 BASELINE.json's weak-scaling sweep at 1,048,576 samples per GPU (the only listed config that is both a training
 workload and defined for 1/2/4/8 GPUs); the other configs are parity-test cases and optional --workload values.
 """
@@ -35,6 +38,10 @@ WORKLOADS = {
     "plus_hint_4_full": dict(d=100, dc=0, n_blocks=4, c_internal=[263, 131, 65, 32, 32], max_splits=-1, batch=10000),
     "plus_cond_recursive_4": dict(d=100, dc=4, n_blocks=4, c_internal=[267, 133, 66], max_splits=-1, batch=10000),
 }
+# every BASELINE.json workload at its stated batch: plus_shape at 500 (BASELINE text) and 10 000 (the configs' own)
+CONFIG_SWEEP = [("plus_hint_4_3", 500), ("plus_hint_4_3", 10000), ("plus_hint_4_full", 10000), ("plus_cond_recursive_4", 10000),
+                ("lens_hint_8_full", 10000), ("lens_concat_cond", 10000), ("power_hint_8", 1 << 16), ("gas_hint_8", 1 << 18),
+                ("miniboone_hint_8", 1 << 18), ("d43_hint_8", 1 << 20)]
 METRIC = "samples/sec (train step: fwd+logdet, NLL, backward, clamp, Adam)"
 ADAM = dict(lr=0.01, betas=(0.9, 0.95), eps=1e-4, weight_decay=1.86e-5)  # miniboone_hint_8.py:38-44, train_unconditional.py:174-176
 
@@ -184,11 +191,58 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def measure_tf32_peak(torch, dev):
+    """TF32 dense tensor-pipe peak of THIS box: torch.matmul (cuBLAS, allow_tf32) 8192^3, same method as MEASURED_PEAKS.json's
+    bf16 figures: best single launch of 10 (burst) and back-to-back launches for ~1.5 s (sustained).  A yardstick only."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        out = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=out)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=out); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(20, int(1500.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return {"burst_tflops": fl / (best * 1e-3) / 1e12, "sustained_tflops": fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 inputs, allow_tf32, {n}^3: best of 10 single launches (burst), {reps} back-to-back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b, out
+
+
+def bwd_kernel_name(plan, mode):
+    if mode == "fp32" or mode == "tf32_tcgen05":
+        return "hint_bwd_fp32_kernel"
+    if mode == "tf32x3":
+        return "hint_bwd_mma_kernel<TM,3xTF32>"
+    if mode in ("tf32", "tf32_chain") and plan.mode_supported("tf32_chain"):
+        return "hint_bwd_chain_kernel<MT=1,NW=4> (register-chained warp-MMA)"
+    if mode in ("tf32", "tf32_tc3") and plan.mode_supported("tf32_tc3"):
+        return "hint_tc3_bwd_kernel (tcgen05 / TMEM)"
+    return "hint_bwd_mma_kernel<TM,TF32>"
+
+
 def run_ours(args, w, name):
     import torch
     import torch.distributed as dist
     import hint_b200
-    from hint_b200 import HintFlow, nll_loss, BucketedGradAllReduce, broadcast_parameters
+    from hint_b200 import HintFlow, nll_loss, BucketedGradAllReduce, broadcast_parameters, FusedClampAdam, FusedTrainStep
+    from hint_b200 import _lib as hlib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,30 +254,8 @@ def run_ours(args, w, name):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    hint_b200.set_precision(args.mode)
-    B = args.batch or w["batch"]
-    torch.manual_seed(0)
-    model = HintFlow(w["d"], w["n_blocks"], w["c_internal"], dims_c=[(w["dc"],)] if w["dc"] else [],
-                     max_splits=w["max_splits"]).to(dev)
-    model.init_like_reference_scripts(0.005)
-    broadcast_parameters(model)
-    params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, fused=True, **ADAM)
-    reducer = BucketedGradAllReduce(model)
-    x, c = synthetic_batch(torch, B, w["d"], w["dc"], dev, 1 + rank)
-    loss_acc = torch.zeros((), device=dev)
-
-    def train_step(xb, cb):
-        opt.zero_grad(set_to_none=True)
-        xn = xb + 0.01 * torch.randn_like(xb)
-        z, J = model(xn, cb)
-        loss = nll_loss(z, J)
-        loss.backward()
-        reducer.finish()
-        for p in params:
-            p.grad.clamp_(-5.0, 5.0)
-        opt.step()
-        return loss
+    lib = hlib.load()
+    launches = lambda: int(lib.hint_launch_count())
 
     def barrier():
         if world > 1:
@@ -244,47 +276,124 @@ def run_ours(args, w, name):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    flush = None
-    if B * w["d"] * 4 <= 126e6:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def timed_avg(fn, steps):
-        """ms per call; when the inputs fit in L2 every call is timed alone with an L2 flush before it."""
-        if flush is None:
-            return timed(fn, steps) / steps
-        total = 0.0
-        for _ in range(steps):
-            flush.zero_()
-            total += timed(fn, 1)
-        return total / steps
+    def make_timed_avg(in_l2):
+        def timed_avg(fn, steps):
+            """ms per call; when the inputs fit in L2 every call is timed alone with an L2 flush before it."""
+            if not in_l2:
+                return timed(fn, steps) / steps
+            total = 0.0
+            for _ in range(steps):
+                flush_buf.zero_()
+                total += timed(fn, 1)
+            return total / steps
+        return timed_avg
 
-    # ---- training step, batch resident in HBM ----------------------------------------------------------------
+    def build(wl, B, mode, seed_rank=True):
+        hint_b200.set_precision(mode)
+        torch.manual_seed(0)
+        model = HintFlow(wl["d"], wl["n_blocks"], wl["c_internal"], dims_c=[(wl["dc"],)] if wl["dc"] else [],
+                         max_splits=wl["max_splits"]).to(dev)
+        model.init_like_reference_scripts(0.005)
+        broadcast_parameters(model)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = FusedClampAdam(params, grad_clamp=5.0, **ADAM)
+        trainer = FusedTrainStep(model, opt, noise=0.01, seed=1234 + rank)
+        x, c = synthetic_batch(torch, B, wl["d"], wl["dc"], dev, 1 + (rank if seed_rank else 0))
+        return model, params, opt, trainer, x, c
+
+    def phases(wl, B, mode, steps, warmup):
+        """train step / fwd+logdet / inverse of one workload: samples/s (whole job) and the launch count of one train step."""
+        model, params, opt, trainer, x, c = build(wl, B, mode)
+        tavg = make_timed_avg(B * wl["d"] * 4 <= 126e6)
+        for _ in range(warmup):
+            trainer.step(x, c)
+        n0 = launches()
+        ms_t = tavg(lambda: trainer.step(x, c), steps)
+        per_step = (launches() - n0) // steps
+        out = {"train_samples_per_s": B * world / (ms_t * 1e-3), "train_ms": ms_t, "launches_per_train_step": per_step}
+        with torch.no_grad():
+            z0, _ = model(x, c)
+            for nm, fn in (("fwd_logdet", lambda: model(x, c)), ("inverse", lambda: model(z0, c, rev=True))):
+                fn()
+                ms = tavg(fn, steps)
+                out[nm + "_samples_per_s"] = B * world / (ms * 1e-3)
+                out[nm + "_ms"] = ms
+        out["flops_per_sample_fwd"] = model.flops_per_sample
+        return out, (model, params, opt, trainer, x, c)
+
+    B = args.batch or w["batch"]
+    tf32_peak = measure_tf32_peak(torch, dev) if rank == 0 else None
+    hint_b200.set_precision(args.mode)
+    model, params, opt, trainer, x, c = build(w, B, args.mode)
+    timed_avg = make_timed_avg(B * w["d"] * 4 <= 126e6)
+
+    # ---- training step, batch resident in HBM: the library's fused step (noise, forward, NLL, backward, [all-reduce], clamp+Adam) ----
+    last_loss = [None]
+
     def step_resident():
-        loss_acc.add_(train_step(x, c).detach())
+        last_loss[0] = trainer.step(x, c)
 
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    n0 = launches()
     ms_step = timed_avg(step_resident, args.steps)
+    gpu_launches = launches() - n0
     clocks = sampler.stop() if sampler else None
     value = B * world / (ms_step * 1e-3)
+    final_loss = float(last_loss[0][0].item())
 
-    # ---- end to end: host batch (pinned) -> H2D -> step -> D2H of the loss, every step ------------------------
+    # ---- end to end: pinned host batch -> H2D (copy stream, double-buffered prefetch) -> step -> D2H of the loss, every step ----------
     xh = x.cpu().pin_memory()
     ch = c.cpu().pin_memory() if c is not None else None
     h2d = xh.numel() * 4 + (ch.numel() * 4 if ch is not None else 0)
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty_like(x) for _ in range(2)]
+    cbuf = [torch.empty_like(c) for _ in range(2)] if c is not None else [None, None]
+    loss_host = torch.zeros(2, 3).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]      # H2D of slot i finished
+    consumed = [torch.cuda.Event() for _ in range(2)]   # the step that read slot i finished
+    loss_done = [torch.cuda.Event() for _ in range(2)]
 
-    def step_e2e():
-        xb = xh.to(dev, non_blocking=True)
-        cb = ch.to(dev, non_blocking=True) if ch is not None else None
-        train_step(xb, cb).item()
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            xbuf[slot].copy_(xh, non_blocking=True)
+            if ch is not None:
+                cbuf[slot].copy_(ch, non_blocking=True)
+            ready[slot].record(copy_stream)
 
-    step_e2e()
-    ms_e2e = timed_avg(step_e2e, args.steps)
-    e2e = {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-           "ms_per_step": ms_e2e}
+    def run_e2e(steps):
+        """Every step: its own H2D copy of the batch (prefetched one step ahead on the copy stream) and a D2H read of its loss
+        (read on the host one step later, so the host never drains the GPU queue).  All copies are inside the timed region."""
+        cur = torch.cuda.current_stream()
+        for sl in range(2):
+            consumed[sl].record(cur)
+        prefetch(0)
+        for i in range(steps):
+            sl = i & 1
+            if i + 1 < steps:
+                prefetch(sl ^ 1)
+            cur.wait_event(ready[sl])
+            l3 = trainer.step(xbuf[sl], cbuf[sl])
+            consumed[sl].record(cur)
+            loss_host[sl].copy_(l3, non_blocking=True)
+            loss_done[sl].record(cur)
+            if i > 0:
+                loss_done[sl ^ 1].synchronize()
+                float(loss_host[sl ^ 1][0])
+        loss_done[(steps - 1) & 1].synchronize()
+        float(loss_host[(steps - 1) & 1][0])
+
+    run_e2e(2)
+    ms_e2e = timed(lambda: run_e2e(args.steps), 1) / args.steps
+    e2e = {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+           "ms_per_step": ms_e2e, "how": "FusedTrainStep.step on a batch copied from pinned host memory every step (copy stream, one "
+                                         "step of prefetch) + D2H of the 3-float loss every step"}
 
     # ---- forward+logdet and inverse (no grad, no collective) --------------------------------------------------
     extra = {}
@@ -303,6 +412,28 @@ def run_ours(args, w, name):
     extra["train_tflops_algorithmic"] = 3 * F * value / 1e12
     extra["fwd_tflops_algorithmic"] = F * extra["fwd_logdet_samples_per_s"] / 1e12
 
+    # ---- the reference-surface path (nn.Module forward + torch autograd + clamp_ + torch Adam), for comparison ------------------
+    opt_t = torch.optim.Adam(params, fused=True, **ADAM)
+    reducer = BucketedGradAllReduce(model)
+
+    def autograd_step():
+        opt_t.zero_grad(set_to_none=True)
+        z, J = model(x + 0.01 * torch.randn_like(x), c)
+        loss = nll_loss(z, J)
+        loss.backward()
+        reducer.finish()
+        for p in params:
+            p.grad.clamp_(-5.0, 5.0)
+        opt_t.step()
+
+    autograd_step()
+    ms_ag = timed_avg(autograd_step, max(2, args.steps // 2))
+    reducer.remove()
+    extra["autograd_path_train_samples_per_s"] = B * world / (ms_ag * 1e-3)
+    extra["autograd_path_note"] = "same step through HierarchicalAffineCouplingBlock.forward + loss.backward() + clamp_ + torch.optim.Adam(fused)"
+    for p in params:
+        p.grad = torch.zeros_like(p)   # the fused trainer writes gradients in place
+
     # ---- roofline of the dominant kernel: the fused backward of one block -------------------------------------
     blk = model.blocks[0]
     with torch.no_grad():
@@ -317,35 +448,80 @@ def run_ours(args, w, name):
         run_f()
         ms_f = timed_avg(run_f, args.steps)
     peaks, peak_src = measured_peaks()
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    if tf32_peak is None:
+        tf32_peak = {"burst_tflops": peaks["bf16_tflops"] / 2.0, "sustained_tflops": peaks["bf16_tflops_sustained"] / 2.0,
+                     "how": "bf16 figures of MEASURED_PEAKS.json / 2"}
+    peak_alone = tf32_peak["burst_tflops"]          # a kernel timed alone
+    peak_step = tf32_peak["sustained_tflops"]       # work timed inside a long step
     Fb = blk.plan.flops_per_sample
     achieved = 2 * Fb * B / (ms_b * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(name, {}).get("bwd_dram_bytes_per_launch")
-    kname = {"fp32": "hint_bwd_fp32_kernel", "tf32_tcgen05": "hint_bwd_fp32_kernel", "tf32x3": "hint_bwd_mma_kernel<TM,3xTF32>"}.get(
-        args.mode, "hint_bwd_mma_kernel<TM,TF32>")
-    chain = args.mode in ("tf32", "tf32_chain") and blk.plan.mode_supported("tf32_chain") and os.environ.get("HINT_B200_TF32_BWD") != "mma"
-    if chain:
-        kname = "hint_bwd_chain_kernel<MT=1,NW=4> (register-chained warp-MMA)"
-    # second denominator: what mma.sync.m16n8k8 tf32 itself sustains on this chip (profiles/ubench5_r01_mma_sync_tf32.txt);
-    # the kernels of this path issue warp-level MMAs, tcgen05 does not fit the 8..72-wide layers
-    mma_sync_peak = 270.0
+    mma_sync_peak = 270.0   # profiles/ubench5_r01_mma_sync_tf32.txt: what mma.sync.m16n8k8 tf32 sustains on this chip
+    kname = bwd_kernel_name(blk.plan, args.mode)
+    fp32_mode = args.mode == "fp32"
     roofline = {"bound": "tensor", "kernel": f"{kname} (one block, B={B})", "achieved": achieved,
-                "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic,
-                "peak_source": f"TF32 dense = bf16_tflops_sustained/2 of {peak_src}",
+                "peak": peak_alone, "unit": "TFLOP/s", "frac": achieved / peak_alone, "traffic": traffic,
+                "peak_source": "TF32 dense, measured on this box in this run (burst: the kernel is timed alone): " + tf32_peak["how"],
+                "tf32_peak_measured": tf32_peak,
                 "flops_per_launch": 2 * Fb * B, "ms_per_launch": ms_b,
+                "algorithmic_bytes_per_launch": 4 * (3 * w["d"] + 1 + w["dc"]) * B,
                 "frac_of_mma_sync_tf32_peak": achieved / mma_sync_peak, "mma_sync_tf32_peak_tflops": mma_sync_peak,
-                "fwd_kernel": {"achieved": Fb * B / (ms_f * 1e-3) / 1e12, "ms_per_launch": ms_f},
+                "phases": {
+                    "train_step": {"tflops": 3 * F * value / world / 1e12, "frac": 3 * F * value / world / 1e12 / peak_step},
+                    "fwd_logdet": {"tflops": F * extra["fwd_logdet_samples_per_s"] / world / 1e12,
+                                   "frac": F * extra["fwd_logdet_samples_per_s"] / world / 1e12 / peak_step},
+                    "inverse": {"tflops": F * extra["inverse_samples_per_s"] / world / 1e12,
+                                "frac": F * extra["inverse_samples_per_s"] / world / 1e12 / peak_step},
+                    "peak": peak_step, "peak_kind": "TF32 sustained (phases are timed inside long steps), per GPU"},
+                "fwd_kernel": {"achieved": Fb * B / (ms_f * 1e-3) / 1e12, "ms_per_launch": ms_f, "frac": Fb * B / (ms_f * 1e-3) / 1e12 / peak_alone},
                 "hbm_gbs_fwd_streaming": (2 * w["d"] + 1 + w["dc"]) * 4 * B / (ms_f * 1e-3) / 1e9,
-                "note": "launch = pack + fused kernel (+ partial-gradient reduce), timed with CUDA events on the launch stream"}
+                "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                "note": ("launch = pack + fused kernel (+ partial-gradient reduce), timed with CUDA events on the launch stream"
+                         + ("; fp32 mode runs on CUDA cores: the tensor peak is not its bound" if fp32_mode else ""))}
 
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.mode,
             "data": "synthetic", "config": workload_config(name, w, B, world), "roofline": roofline, "e2e": e2e,
-            "gpu_launches": args.steps * w["n_blocks"] * 5, "clocks": clocks, "extra": extra,
-            "final_loss": float(loss_acc.item()) / max(1, args.steps + args.warmup)}
+            "gpu_launches": gpu_launches, "gpu_launches_how": "hint_launch_count() (C ABI) after - before the timed region: every kernel "
+            "this library launched; the step launches no torch kernels" + (" (NCCL all-reduces excluded)" if world > 1 else ""),
+            "clocks": clocks, "extra": extra, "final_loss": final_loss}
+
+    # ---- the other arithmetic modes on the same workload, and every BASELINE workload at its stated batch (1 GPU only) ----------
+    if world == 1 and not args.quick:
+        del model, params, opt, trainer, opt_t
+        modes = {}
+        for md in ("fp32", "tf32x3"):
+            if md == args.mode:
+                continue
+            try:
+                ph, keep = phases(w, B, md, 3, 3)
+                del keep
+                modes[md] = {k: ph[k] for k in ("train_samples_per_s", "train_ms", "fwd_logdet_samples_per_s", "inverse_samples_per_s")}
+            except Exception as e:   # a mode outside a kernel family's envelope is reported, not fatal
+                modes[md] = {"error": str(e)[:200]}
+        line["modes"] = modes
+        cfgs = []
+        for wn, Bw in CONFIG_SWEEP:
+            if wn == name and Bw == B:
+                continue
+            wl = WORKLOADS[wn]
+            try:
+                ph, keep = phases(wl, Bw, args.mode, 3, 3)
+                plan0 = keep[0].blocks[0].plan
+                entry = {"workload": wn, "batch": Bw, "bwd_kernel": bwd_kernel_name(plan0, args.mode)}
+                del keep
+                entry.update(ph)
+                entry["train_tflops_algorithmic"] = 3 * ph["flops_per_sample_fwd"] * ph["train_samples_per_s"] / 1e12
+                entry["train_frac_of_tf32_peak"] = entry["train_tflops_algorithmic"] / peak_step
+                entry["fwd_frac_of_tf32_peak"] = ph["flops_per_sample_fwd"] * ph["fwd_logdet_samples_per_s"] / 1e12 / peak_step
+                cfgs.append(entry)
+            except Exception as e:
+                cfgs.append({"workload": wn, "batch": Bw, "error": str(e)[:200]})
+        line["configs"] = cfgs
+        hint_b200.set_precision(args.mode)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = min(B, args.cpu_sample)
@@ -370,9 +546,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d43_hint_8", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
-    ap.add_argument("--mode", default=os.environ.get("HINT_B200_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3", "tf32_mma", "tf32_tcgen05"])
+    ap.add_argument("--mode", default=os.environ.get("HINT_B200_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3", "tf32_mma", "tf32_tcgen05", "tf32_chain", "tf32_tc3"])
     ap.add_argument("--cpu-sample", type=int, default=32768, help="samples per CPU step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the extra modes and the sweep over the other BASELINE workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

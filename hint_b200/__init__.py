@@ -7,9 +7,11 @@ from .block import (HierarchicalAffineCouplingBlock, HierarchicalAffineCouplingT
                     linear_subnet_constructor, set_precision, get_precision)
 from .model import HintFlow, nll_loss
 from .parallel import BucketedGradAllReduce, broadcast_parameters, shard_rows
+from .train import FusedClampAdam, FusedTrainStep, add_noise, nll_loss_fused
 
 __version__ = _lib.load().hint_version().decode()
 
 __all__ = ["HierarchicalAffineCouplingBlock", "HierarchicalAffineCouplingTree", "TreePlan",
            "linear_subnet_constructor", "set_precision", "get_precision", "HintFlow", "nll_loss",
-           "BucketedGradAllReduce", "broadcast_parameters", "shard_rows"]
+           "BucketedGradAllReduce", "broadcast_parameters", "shard_rows",
+           "FusedClampAdam", "FusedTrainStep", "add_noise", "nll_loss_fused"]

@@ -18,7 +18,8 @@ EXPORTS = [
     "hint_plan_create", "hint_plan_destroy", "hint_plan_num_nodes", "hint_plan_node", "hint_plan_param_count",
     "hint_plan_param_layout", "hint_plan_flops_per_sample", "hint_plan_tile_rows", "hint_plan_mode_supported",
     "hint_workspace_bytes",
-    "hint_forward", "hint_backward", "hint_last_error", "hint_version",
+    "hint_forward", "hint_backward", "hint_last_error", "hint_version", "hint_launch_count",
+    "hint_backward_nll", "hint_add_noise", "hint_nll_workspace_bytes", "hint_nll_loss", "hint_adam_step",
 ]
 
 
@@ -84,6 +85,20 @@ def load():
     lib.hint_backward.restype = ctypes.c_int
     lib.hint_backward.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, i64, i32, f32p, f32p, f32p, f32p, vp,
                                   ctypes.c_size_t, vp]
+    f32 = ctypes.c_float
+    lib.hint_backward_nll.restype = ctypes.c_int
+    lib.hint_backward_nll.argtypes = [vp, f32p, f32p, f32p, f32p, f32, i64, i32, f32p, f32p, f32p, f32p, vp, ctypes.c_size_t, vp]
+    lib.hint_add_noise.restype = ctypes.c_int
+    lib.hint_add_noise.argtypes = [f32p, f32p, i64, f32, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.hint_nll_workspace_bytes.restype = ctypes.c_size_t
+    lib.hint_nll_workspace_bytes.argtypes = []
+    lib.hint_nll_loss.restype = ctypes.c_int
+    lib.hint_nll_loss.argtypes = [f32p, ctypes.POINTER(vp), i32, i64, i32, f32p, vp, ctypes.c_size_t, vp]
+    lib.hint_adam_step.restype = ctypes.c_int
+    lib.hint_adam_step.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                   ctypes.POINTER(i64), f32, f32, f32, f32, f32, f32, i64, vp]
+    lib.hint_launch_count.restype = ctypes.c_uint64
+    lib.hint_launch_count.argtypes = []
     lib.hint_last_error.restype = ctypes.c_char_p
     lib.hint_last_error.argtypes = []
     lib.hint_version.restype = ctypes.c_char_p

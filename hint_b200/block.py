@@ -144,12 +144,28 @@ class TreePlan:
                                               ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
         return z, J
 
-    def backward(self, z, c, flat, dz, dJ, mode=None, want_xrec=False, want_dc=True):
-        """Gradients of the rev=False direction from the block OUTPUT z (memory-free backward)."""
+    def backward(self, z, c, flat, dz, dJ, mode=None, want_xrec=False, want_dc=True, nll_scale=None, out=None):
+        """Gradients of the rev=False direction from the block OUTPUT z (memory-free backward).
+
+        ``nll_scale`` (dJ = None): the upstream gradient is the NLL loss's (train_unconditional.py:128-132): dlogdet = -nll_scale
+        and, when dz is None too (last block), dz = nll_scale * z - both generated inside the kernel (hint_backward_nll) where
+        the kernel family supports it and materialised here otherwise.  ``out``: optional tensor receiving the parameter gradient."""
         B = z.shape[0]
         self._check(z, "z", (B, self.d))
+        if nll_scale is not None:
+            if dz is not None:
+                self._check(dz, "dz", (B, self.d))
+            try:
+                return self._backward_launch(z, c, flat, dz, None, mode, want_xrec, want_dc, float(nll_scale), out)
+            except NotImplementedError:   # kernel family without the fused form: materialise the two gradients
+                dz = z * float(nll_scale) if dz is None else dz
+                dJ = torch.full((B,), -float(nll_scale), dtype=torch.float32, device=z.device)
         self._check(dz, "dz", (B, self.d))
         self._check(dJ, "dlogdet", (B,))
+        return self._backward_launch(z, c, flat, dz, dJ, mode, want_xrec, want_dc, None, out)
+
+    def _backward_launch(self, z, c, flat, dz, dJ, mode, want_xrec, want_dc, nll_scale, out):
+        B = z.shape[0]
         self._check(flat, "params", (self.n_params,))
         if self.dc:
             self._check(c, "c", (B, self.dc))
@@ -159,16 +175,22 @@ class TreePlan:
             dx = torch.empty_like(z)
             dc = torch.empty(B, self.dc, dtype=torch.float32, device=z.device) if (self.dc and want_dc) else None
             xrec = torch.empty_like(z) if want_xrec else None
-            dflat = torch.empty_like(flat)
+            dflat = out if (out is not None and out.is_contiguous() and out.data_ptr() % 16 == 0 and out.shape == flat.shape) else torch.empty_like(flat)
             nbytes = self._lib.hint_workspace_bytes(self._h, B, _lib.WS_BACKWARD)
             if nbytes == 0:
                 _lib.check(_lib.HINT_ERR_CUDA)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
-            _lib.check(self._lib.hint_backward(self._h, z.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(),
-                                               dz.data_ptr(), dJ.data_ptr(), B, _MODES[mode or _mode],
-                                               xrec.data_ptr() if want_xrec else None, dx.data_ptr(),
-                                               dc.data_ptr() if dc is not None else None, dflat.data_ptr(),
-                                               ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+            tail = (xrec.data_ptr() if want_xrec else None, dx.data_ptr(), dc.data_ptr() if dc is not None else None,
+                    dflat.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+            if nll_scale is not None:
+                _lib.check(self._lib.hint_backward_nll(self._h, z.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(),
+                                                       dz.data_ptr() if dz is not None else None, nll_scale, B, _MODES[mode or _mode], *tail))
+            else:
+                _lib.check(self._lib.hint_backward(self._h, z.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(),
+                                                   dz.data_ptr(), dJ.data_ptr(), B, _MODES[mode or _mode], *tail))
+            if out is not None and dflat is not out:
+                out.copy_(dflat)
+                dflat = out
         return dx, dc, dflat, xrec
 
 

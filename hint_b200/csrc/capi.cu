@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 
+#include "launch_count.h"
 #include "plan.h"
 #include "plan_tc.h"
 #include "plan_mma.h"
@@ -18,11 +19,16 @@
 #include "chain_launch.h"
 #include "plan_tc3.h"
 #include "tc3_launch.h"
+#include "train_ops.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc2_kernels.cuh"
 
 using namespace hint;
+
+namespace hint {
+std::atomic<unsigned long long> g_launches{0};
+}
 
 namespace {
 
@@ -184,7 +190,7 @@ int pack_weights(const hint_plan* hp, const DevPlan& d, const float* params, flo
     const long long n = hp->p.n_packed;
     const int threads = 256;
     const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-    hint_pack_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, n);
+    hint_pack_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, n); HINT_LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return HINT_OK;
 }
@@ -251,7 +257,9 @@ int hint_dev_tc3_debug(hint_plan_t* hp, int32_t n_epi_limit, const float* z, con
     for (size_t i = 0; i < sizeof(L) / 4; ++i) layout[i] = L[i];
     return HINT_OK;
 }
-const char* hint_version(void) { return "hint_b200 0.1 sm_100a"; }
+const char* hint_version(void) { return "hint_b200 0.2 sm_100a"; }
+
+uint64_t hint_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 
 int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n_internal, double clamp,
                      int32_t max_splits, int32_t min_split_size, int32_t reshuffle, hint_plan_t** out) {
@@ -416,7 +424,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         {
             const int threads = 256;
             const int blocks = (int)std::min<long long>((t.n_packed + threads - 1) / threads, 148 * 8);
-            hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats);
+            hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats); HINT_LAUNCHED();
             CUDA_TRY(cudaGetLastError());
         }
         static const bool force_v1 = std::getenv("HINT_B200_TC_V1") != nullptr;
@@ -430,8 +438,8 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
                 CUDA_TRY(cudaMemsetAsync(dbg2, 0, 16 * sizeof(long long), st));
             }
             long long* dp = dbg_on ? dbg2 : nullptr;
-            if (rev) hint_tc2_kernel<true><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp);
-            else hint_tc2_kernel<false><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp);
+            if (rev) { hint_tc2_kernel<true><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp); HINT_LAUNCHED(); }
+            else { hint_tc2_kernel<false><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp); HINT_LAUNCHED(); }
             CUDA_TRY(cudaGetLastError());
             if (dbg_on) {
                 long long h[16];
@@ -465,8 +473,8 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         }
         const long long ntiles = (B + 127) / 128;
         const int grid = (int)std::min<long long>(ntiles, d->num_sms);
-        if (rev) hint_fwd_tf32_kernel<true><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
-        else hint_fwd_tf32_kernel<false><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B);
+        if (rev) { hint_fwd_tf32_kernel<true><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B); HINT_LAUNCHED(); }
+        else { hint_fwd_tf32_kernel<false><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B); HINT_LAUNCHED(); }
         CUDA_TRY(cudaGetLastError());
         if (dbg) {
             long long h[16];
@@ -486,7 +494,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     const int grid = (int)std::min<long long>(ntiles, d->fwd.max_ctas);
 #define LAUNCH_FWD(TMV)                                                                                   \
     case TMV:                                                                                             \
-        hint_fwd_fp32_kernel<TMV><<<grid, kThreads, s.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B, rev ? 1 : 0); \
+        hint_fwd_fp32_kernel<TMV><<<grid, kThreads, s.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B, rev ? 1 : 0); HINT_LAUNCHED(); \
         break;
     switch (s.TM) {
         LAUNCH_FWD(128) LAUNCH_FWD(64) LAUNCH_FWD(32) LAUNCH_FWD(16) LAUNCH_FWD(8)
@@ -497,9 +505,11 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     return HINT_OK;
 }
 
-int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const float* params, const float* dz,
-                  const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
-                  void* workspace, size_t workspace_bytes, void* stream) {
+// nll_scale != 0 (with dz == dlogdet == NULL): the upstream gradient is generated in the tile load, dz = nll_scale * z and
+// dlogdet = -nll_scale (hint_backward_nll); only the kernel families that implement it accept that form.
+static int backward_impl(const hint_plan_t* hp_c, const float* z, const float* c, const float* params, const float* dz,
+                         const float* dlogdet, float nll_scale, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
+                         void* workspace, size_t workspace_bytes, void* stream) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
     // HINT_MODE_TF32_TCGEN05 has no backward kernel of its own: it runs the FP32 CUDA-core sweep (which differentiates
     // the exact function at the TF32-computed output).
@@ -518,7 +528,10 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
         CUDA_TRY(cudaMemsetAsync(dparams, 0, (size_t)hp->p.n_params * 4, st));
         return HINT_OK;
     }
-    if (!dz || !dlogdet || !dx) return fail(HINT_ERR_INVALID, "NULL gradient pointer");
+    const bool nll = nll_scale != 0.f;
+    if ((!nll && (!dz || !dlogdet)) || !dx) return fail(HINT_ERR_INVALID, "NULL gradient pointer");
+    if (nll && !(mode == HINT_MODE_TF32_TC3 || mode == HINT_MODE_TF32_CHAIN || (mode == HINT_MODE_TF32 && (use_chain || hp->tc3.ok))))
+        return fail(HINT_ERR_UNSUPPORTED, "the fused NLL gradient exists in the register-chained and tcgen05 training kernels only");
     if (!aligned16(dz) || !aligned16(dx) || !aligned16(dc) || !aligned16(x_rec) || !aligned16(workspace))
         return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
     DevPlan* d = nullptr;
@@ -531,18 +544,18 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->tc3.n_packed * 4));
         CUDA_TRY(tc3_pack(hp->tc3, d->tc3, params, packed, st));
         const int grid = tc3_bwd_ctas(d->tc3, (long long)B);
-        CUDA_TRY(tc3_launch_bwd(hp->tc3, d->tc3, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, dparams, (long long)B, st));
+        CUDA_TRY(tc3_launch_bwd(hp->tc3, d->tc3, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, dparams, (long long)B, st, nullptr, nll_scale));
         return HINT_OK;
     }
     if (use_chain) {
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)hp->chain.n_packed * 4));
         CUDA_TRY(chain_pack(hp->chain, d->chain, params, packed, st));
         const int grid = chain_bwd_ctas(hp->chain, d->chain, (long long)B);
-        CUDA_TRY(chain_launch_bwd(hp->p, hp->chain, d->chain, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, (long long)B, st));
+        CUDA_TRY(chain_launch_bwd(hp->p, hp->chain, d->chain, grid, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, (long long)B, st, nll_scale));
         const long long n = hp->p.n_params;
         const int threads = 256;
         const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->chain.unpack_src, partials, grid, (long long)hp->chain.n_partial, dparams, n);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->chain.unpack_src, partials, grid, (long long)hp->chain.n_partial, dparams, n); HINT_LAUNCHED();
         CUDA_TRY(cudaGetLastError());
         return HINT_OK;
     }
@@ -558,7 +571,7 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
         const long long n = hp->p.n_params;
         const int threads = 256;
         const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->mma.unpack_src, partials, grid, np, dparams, n);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->mma.unpack_src, partials, grid, np, dparams, n); HINT_LAUNCHED();
         CUDA_TRY(cudaGetLastError());
         return HINT_OK;
     }
@@ -570,7 +583,7 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
 #define LAUNCH_BWD(TMV)                                                                                        \
     case TMV:                                                                                                  \
         hint_bwd_fp32_kernel<TMV><<<grid, kThreads, s.smem_bytes, st>>>(T, z, c, packed, dz, dlogdet, x_rec, dx, dc, partials, \
-                                                                         (long long)hp->p.n_partial, (long long)B); \
+                                                                         (long long)hp->p.n_partial, (long long)B); HINT_LAUNCHED(); \
         break;
     switch (s.TM) {
         LAUNCH_BWD(128) LAUNCH_BWD(64) LAUNCH_BWD(32) LAUNCH_BWD(16) LAUNCH_BWD(8)
@@ -582,9 +595,50 @@ int hint_backward(const hint_plan_t* hp_c, const float* z, const float* c, const
         const long long n = hp->p.n_params;
         const int threads = 256;
         const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->unpack_src, partials, grid, (long long)hp->p.n_partial, dparams, n);
+        hint_reduce_unpack_kernel<<<blocks, threads, 0, st>>>(d->unpack_src, partials, grid, (long long)hp->p.n_partial, dparams, n); HINT_LAUNCHED();
         CUDA_TRY(cudaGetLastError());
     }
+    return HINT_OK;
+}
+
+int hint_backward(const hint_plan_t* hp, const float* z, const float* c, const float* params, const float* dz,
+                  const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (B > 0 && (!dz || !dlogdet)) return fail(HINT_ERR_INVALID, "NULL gradient pointer");
+    return backward_impl(hp, z, c, params, dz, dlogdet, 0.f, B, mode, x_rec, dx, dc, dparams, workspace, workspace_bytes, stream);
+}
+
+int hint_backward_nll(const hint_plan_t* hp, const float* z, const float* c, const float* params, const float* dz, float grad_scale,
+                      int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!(grad_scale != 0.f)) return fail(HINT_ERR_INVALID, "grad_scale must be non-zero (1/B for the mean NLL)");
+    return backward_impl(hp, z, c, params, dz, nullptr, grad_scale, B, mode, x_rec, dx, dc, dparams, workspace, workspace_bytes, stream);
+}
+
+int hint_add_noise(const float* x, float* out, int64_t n, float sigma, uint64_t seed, uint64_t offset, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(HINT_ERR_INVALID, "bad noise arguments");
+    CUDA_TRY(train_add_noise(x, out, (long long)n, sigma, seed, offset, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+size_t hint_nll_workspace_bytes(void) { return train_nll_workspace_bytes(); }
+
+int hint_nll_loss(const float* z, const float* const* logdets, int32_t n_logdets, int64_t B, int32_t d, float* loss3, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    if (B <= 0 || d <= 0 || !z || !logdets || n_logdets < 1 || n_logdets > 64 || !loss3) return fail(HINT_ERR_INVALID, "bad NLL arguments");
+    if (!workspace || workspace_bytes < train_nll_workspace_bytes()) return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    CUDA_TRY(train_nll_loss(z, logdets, n_logdets, (long long)B, d, loss3, workspace, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+int hint_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_clamp, int64_t step, void* stream) {
+    if (n_tensors < 0 || (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes)))
+        return fail(HINT_ERR_INVALID, "bad optimizer arguments");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t must be long long");
+    CUDA_TRY(train_adam_step(n_tensors, params, grads, exp_avg, exp_avg_sq, reinterpret_cast<const long long*>(sizes), lr, beta1,
+                             beta2, eps, weight_decay, grad_clamp, (long long)step, (cudaStream_t)stream));
     return HINT_OK;
 }
 

@@ -24,6 +24,8 @@ struct ChainTables {
     int n_fwd_packed;   // floats of the forward operand region (staged in shared memory by the WS kernels)
     int exp;            // developer experiments (timing only, WRONG results): 1 no partial flush, 2 no dW GEMMs, 4 all operand
                         // loads hit the first 4 KB of the packed buffer (HINT_B200_CHAIN_EXP)
+    float nll_scale;    // backward only, used when dz == NULL: the upstream gradient is that of the NLL loss of
+                        // train_unconditional.py:128-132, generated in the tile load: dz = nll_scale * z; dlogdet == NULL: dlogdet = -nll_scale
 };
 
 HINT_DEV float c_shfl_xor(float v, int mask) {
@@ -920,10 +922,14 @@ HINT_DEV void c_bwd_body(const ChainTables& T, const ChainNode* nodes, const Cha
         const int rows = (int)((B - row0) < TM ? (B - row0) : TM);
         c_load_tile_sw<TM, NT>(S + L.xt, 0, z, row0, rows, T.d, tid);
         c_load_tile_sw<TM, NT>(S + L.xt, T.d, c, row0, rows, T.dc, tid);
-        c_load_tile_sw<TM, NT>(S + L.dz, 0, dz, row0, rows, T.d, tid);
+        if (dz) c_load_tile_sw<TM, NT>(S + L.dz, 0, dz, row0, rows, T.d, tid);
         for (int i = tid; i < T.dc * TM; i += NT) S[L.dz + (T.d + i / TM) * TM + (i % TM)] = 0.f;
-        for (int i = tid; i < TM; i += NT) S[L.dj + i] = (i < rows) ? dlogdet[row0 + i] : 0.f;
+        for (int i = tid; i < TM; i += NT) S[L.dj + i] = (i < rows) ? (dlogdet ? dlogdet[row0 + i] : -T.nll_scale) : 0.f;
         m_cta_sync();
+        if (!dz) {   // fused NLL gradient: the z tile (same swizzled layout) scaled into the gradient tile; rows past the batch are 0
+            for (int i = tid; i < T.d * TM; i += NT) S[L.dz + i] = T.nll_scale * S[L.xt + i];
+            m_cta_sync();
+        }
         for (int q = T.n_nodes - 1; q >= 0; --q)
             c_node_bwd_dispatch<MT, NW>(nodes + q, T.alpha, W, S, L, partial, first, warp, lane, T.exp);
         if (x_rec) c_store_tile_sw<TM, NT>(S + L.xt, 0, x_rec, row0, rows, T.d, tid);

@@ -1,5 +1,6 @@
 // Launch glue of the register-chained warp-MMA kernels.
 #include "chain_launch.h"
+#include "launch_count.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -116,7 +117,7 @@ cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* param
     const long long n = c.n_packed;
     const int threads = 256;
     const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-    hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, nullptr, n, 1, 0);
+    hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, nullptr, n, 1, 0); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -129,12 +130,12 @@ int chain_bwd_ctas(const ChainPlan& c, const DevChain& d, long long B) {
 
 cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& d, int grid, const float* z, const float* cond,
                              const float* packed, const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc,
-                             float* partials, long long B, cudaStream_t st) {
-    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed, chain_exp()};
+                             float* partials, long long B, cudaStream_t st, float nll_scale) {
+    ChainTables T{c.n_nodes, p.d, p.dc, p.alpha, (int)c.n_fwd_packed, chain_exp(), nll_scale};
     const BwdCfg b{d.bwd_mt, d.bwd_nw};
     const ChainBwdSmem L = bwd_layout(p, c, b);
     const long long np = c.n_partial;
-    hint_bwd_chain_kernel<1, 4, 2><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B);
+    hint_bwd_chain_kernel<1, 4, 2><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B); HINT_LAUNCHED();
     if (T.exp & 32) {   // developer aid: phase-boundary cycle stamps of CTA 0 (HINT_B200_CHAIN_EXP=32)
         static long long h[2048];
         cudaStreamSynchronize(st);
@@ -157,8 +158,8 @@ cudaError_t chain_launch_fwd(const Plan& p, const ChainPlan& c, const DevChain& 
     const int grid = (int)std::min<long long>((ntiles + f.nw - 1) / f.nw, d.num_sms);
 #define HINT_CHAIN_LAUNCH(MT, NW, WS)                                                                                          \
     if (f.mt == MT && f.nw == NW && f.ws == WS) {                                                                              \
-        if (rev) hint_fwd_chain_kernel<MT, NW, true, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B);  \
-        else hint_fwd_chain_kernel<MT, NW, false, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B);     \
+        if (rev) { hint_fwd_chain_kernel<MT, NW, true, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B); HINT_LAUNCHED(); }  \
+        else { hint_fwd_chain_kernel<MT, NW, false, WS != 0><<<grid, 32 * NW, f.smem, st>>>(T, c.param, x, cond, packed, z, logdet, B); HINT_LAUNCHED(); }     \
         return cudaGetLastError();                                                                                             \
     }
     HINT_CHAIN_LAUNCH(1, 12, 1) HINT_CHAIN_LAUNCH(1, 8, 1) HINT_CHAIN_LAUNCH(1, 16, 0)

@@ -27,7 +27,7 @@ cudaError_t chain_pack(const ChainPlan& c, const DevChain& d, const float* param
 int chain_bwd_ctas(const ChainPlan& c, const DevChain& d, long long B);
 cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& d, int grid, const float* z, const float* cond,
                              const float* packed, const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc,
-                             float* partials, long long B, cudaStream_t st);
+                             float* partials, long long B, cudaStream_t st, float nll_scale = 0.f);
 cudaError_t chain_launch_fwd(const Plan& p, const ChainPlan& c, const DevChain& d, const float* x, const float* cond,
                              const float* packed, float* z, float* logdet, long long B, int rev, cudaStream_t st);
 

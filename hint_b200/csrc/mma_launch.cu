@@ -1,5 +1,6 @@
 // Launch glue of the warp-MMA kernels: device tables, occupancy, kernel dispatch over the tile size / precision mode.
 #include "mma_launch.h"
+#include "launch_count.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -126,7 +127,7 @@ cudaError_t mma_pack(const MmaPlan& m, const DevMma& d, const float* params, flo
     const long long n = m.n_packed;
     const int threads = 256;
     const int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148 * 8);
-    hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, hi, lo, n, mma_weight_copies(), mma_copy_stride(m));
+    hint_pack_mma_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, hi, lo, n, mma_weight_copies(), mma_copy_stride(m)); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -141,8 +142,8 @@ cudaError_t mma_launch_fwd(const Plan& p, const MmaPlan& m, const DevMma& d, boo
     const int grid = (int)std::min<long long>(ntiles, d.fwd.max_ctas);
 #define HINT_LAUNCH(TMV)                                                                                                   \
     case TMV:                                                                                                              \
-        if (x3) hint_fwd_mma_kernel<TMV, true><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, x, c, hi, lo, z, logdet, B, rev ? 1 : 0);  \
-        else hint_fwd_mma_kernel<TMV, false><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, x, c, hi, lo, z, logdet, B, rev ? 1 : 0);    \
+        if (x3) { hint_fwd_mma_kernel<TMV, true><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, x, c, hi, lo, z, logdet, B, rev ? 1 : 0); HINT_LAUNCHED(); }  \
+        else { hint_fwd_mma_kernel<TMV, false><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, x, c, hi, lo, z, logdet, B, rev ? 1 : 0); HINT_LAUNCHED(); }    \
         break;
     switch (s.TM) {
         HINT_LAUNCH(64) HINT_LAUNCH(32)
@@ -164,8 +165,8 @@ cudaError_t mma_launch_bwd(const Plan& p, const MmaPlan& m, const DevMma& d, boo
     const long long np = m.n_partial;
 #define HINT_LAUNCH(TMV)                                                                                                   \
     case TMV:                                                                                                              \
-        if (x3) hint_bwd_mma_kernel<TMV, true><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, z, c, hi, lo, dz, dlogdet, x_rec, dx, dc, partials, np, B);  \
-        else hint_bwd_mma_kernel<TMV, false><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, z, c, hi, lo, dz, dlogdet, x_rec, dx, dc, partials, np, B);    \
+        if (x3) { hint_bwd_mma_kernel<TMV, true><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, z, c, hi, lo, dz, dlogdet, x_rec, dx, dc, partials, np, B); HINT_LAUNCHED(); }  \
+        else { hint_bwd_mma_kernel<TMV, false><<<grid, kMmaThreads, s.smem_bytes, st>>>(T, P, z, c, hi, lo, dz, dlogdet, x_rec, dx, dc, partials, np, B); HINT_LAUNCHED(); }    \
         break;
     switch (s.TM) {
         HINT_LAUNCH(64) HINT_LAUNCH(32)

@@ -52,7 +52,19 @@ struct Builder {
     std::vector<int> mtime, etime;      // logical timestamps
     int clock = 0;
     int open_chunk = -1;                // chunk whose records are being emitted
+    // Deferred accumulator flushes.  A flush only reads its accumulator columns, so it may run any time before those columns
+    // are written again: the planner parks it here and re-emits it where the epilogue warps would otherwise idle behind a long
+    // MMA (the hidden-layer GEMMs of the NEXT forward chain), or - at the latest - right before a record that overwrites it.
+    std::vector<std::pair<T3Epi, Acc>> pending;
     Builder(const Plan& p_, T3Plan& t_) : p(p_), t(t_) {}
+    void defer(const T3Epi& e, const Acc& a) { pending.emplace_back(e, a); }
+    void drain(int n) {   // emit up to n parked flushes (oldest first); n < 0: all
+        while (!pending.empty() && n != 0) {
+            push_epi(pending.front().first, pending.front().second);
+            pending.erase(pending.begin());
+            if (n > 0) --n;
+        }
+    }
 
     // ---- weights ----
     // Appends the operand as K slabs (each an independent canonical block that fits one ring slot) and emits the
@@ -123,8 +135,20 @@ struct Builder {
         t.n_mma_instr += 16;
         t.tensor_cycles += 16 * (N / 2);
     }
-    void push_mma(const T3Mma& m, const Acc& a) { t.mmas.push_back(m); macc.push_back(a); mtime.push_back(clock++); }
+    // a record / step that writes columns a parked flush still has to read: the flush goes first (all older ones with it: in-order)
+    void drain_clobbered(const Acc& a) {
+        for (size_t i = pending.size(); i-- > 0;) {
+            bool hit = false;
+            for (const Res& w : a.wr) for (const Res& r : pending[i].second.rd) hit |= overlap(w, r);
+            if (hit) { drain((int)i + 1); break; }
+        }
+    }
+    void push_mma(const T3Mma& m, const Acc& a) {
+        drain_clobbered(a);
+        t.mmas.push_back(m); macc.push_back(a); mtime.push_back(clock++);
+    }
     int push_epi(const T3Epi& e, const Acc& a) {
+        if (e.type != T3E_FLUSH) drain_clobbered(a);
         t.epis.push_back(e); eacc.push_back(a); etime.push_back(clock++);
         return (int)t.epis.size() - 1;
     }
@@ -331,6 +355,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
 
     // ---- programs ----
     Builder b(p, t);
+    const bool defer_flush = true;
     const int IMG_IN = 3, IMG_DOUT = 4;
     const int IMG_H1 = 0, IMG_H2 = 1, IMG_DH2 = t.n_imgs_hidden == 3 ? 2 : 1, IMG_DH1 = 1;
     for (size_t gi = 0; gi < t.groups.size(); ++gi) {
@@ -435,7 +460,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             e.e = std::min(128, g.HP - mt * 128); e.f = g.tab_nodes; e.g = kind; e.h = mt;
             e.c = (kind == T3F_W2 ? g.HP : kind == T3F_W1 ? g.KX : -1);   // first "extra" column (bias / condition block)
             Acc a; a.rd.push_back({R_TMEM, col0, col0 + N});
-            b.push_epi(e, a);
+            if (defer_flush && kind != T3F_W3) b.defer(e, a); else b.push_epi(e, a);   // the dW3 flush already runs behind the dH1 GEMM
         };
         auto fwd_chain = [&](int net, bool images, bool layer3) {
             b.gemm_ts(w1g(net), {{g.tm_ain, g.KA / 8}}, P, true);
@@ -444,6 +469,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
                 const auto& n = p.nodes[g.nodes[q]];
                 b.gemm_ts(w2n(net, q), {{P + g.hoff[q], pad8(n.h) / 8}, {P + g.HP, 1}}, Q + g.hoff[q], q == nn - 1);
             }
+            b.drain(-1);   // parked flushes of the previous backward chain run behind the hidden-layer GEMM just issued
             e_hid(Q, images ? IMG_H2 : -1, false);
             if (layer3) b.gemm_ts(w3g(net), {{Q, g.HP / 8 + 1}}, g.tm_out, true);
         };
@@ -519,6 +545,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         }
         bwd_chain(0);
     }
+    b.drain(-1);
     b.infer_waits();
     t.n_packed = (int64_t)t.pack_src.size();
     if ((int)t.tab16.size() * 2 > tab_bytes || (int)(t.epis.size() * sizeof(T3Epi)) > epi_bytes) return fail("internal: epilogue tables exceed their shared-memory reservation");

@@ -41,6 +41,7 @@ struct T3Prog {
     int img_rows[kT3Imgs];
     int xp, op, d, dc, n_tab16;
     float alpha;
+    float nll_scale;   // used when dz == NULL: dz = nll_scale * z, dlogdet = -nll_scale (fused NLL gradient, train_unconditional.py:128-132)
     const T3Epi* epis;
     const T3Chunk* chunks;
     const int16_t* tab16;
@@ -221,7 +222,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                 for (int i = tid; i < 128 * d; i += 32 * kT3EpiWarps) {
                     const int s = i / d, j = i - s * d;
                     xs_all[s * P.xp + j] = i < nx ? __ldg(gz + i) : 0.f;
-                    gs_all[s * P.xp + j] = i < nx ? __ldg(gdz + i) : 0.f;
+                    gs_all[s * P.xp + j] = i < nx ? (dz ? __ldg(gdz + i) : P.nll_scale * __ldg(gz + i)) : 0.f;
                 }
                 if (dc) {
                     const int nc = rows * dc;
@@ -233,7 +234,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                     }
                 }
             }
-            const float dJ = row < rows ? __ldg(dlogdet + row0 + row) : 0.f;
+            const float dJ = row < rows ? (dlogdet ? __ldg(dlogdet + row0 + row) : -P.nll_scale) : 0.f;
             named_bar_sync(1, 32 * kT3EpiWarps);
             int waited = -1;
             for (int si = 0; si < P.n_epi; ++si, ++estep) {

@@ -1,5 +1,6 @@
 // Launch glue of the tcgen05 training kernel.
 #include "tc3_launch.h"
+#include "launch_count.h"
 
 #include <algorithm>
 #include <cstring>
@@ -55,7 +56,7 @@ void tc3_free(DevTc3& d) {
 cudaError_t tc3_pack(const T3Plan& t, const DevTc3& d, const float* params, float* packed, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)std::min<long long>((t.n_packed + threads - 1) / threads, 148 * 8);
-    hint_tc3_pack_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, t.n_packed);
+    hint_tc3_pack_kernel<<<blocks, threads, 0, st>>>(d.pack_src, params, packed, t.n_packed); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -65,14 +66,22 @@ int tc3_bwd_ctas(const DevTc3& d, long long B) {
 
 cudaError_t tc3_launch_bwd(const T3Plan& t, const DevTc3& d, int grid, const float* z, const float* cond, const float* packed,
                            const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc, float* partials,
-                           float* dparams, long long B, cudaStream_t st, long long* prof) {
-    hint_tc3_bwd_kernel<<<grid, kT3Threads, t.smem_bytes, st>>>(*d.prog, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
-                                                                (long long)t.n_partial, B, nullptr, prof);
+                           float* dparams, long long B, cudaStream_t st, long long* prof, float nll_scale) {
+    if (nll_scale != 0.f) {   // the program travels by value: a per-launch field is a host-side copy (the stored plan stays immutable)
+        T3Prog* P = new T3Prog(*d.prog);
+        P->nll_scale = nll_scale;
+        hint_tc3_bwd_kernel<<<grid, kT3Threads, t.smem_bytes, st>>>(*P, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
+                                                                    (long long)t.n_partial, B, nullptr, prof); HINT_LAUNCHED();
+        delete P;
+    } else {
+        hint_tc3_bwd_kernel<<<grid, kT3Threads, t.smem_bytes, st>>>(*d.prog, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
+                                                                    (long long)t.n_partial, B, nullptr, prof); HINT_LAUNCHED();
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int threads = 256;
     const int blocks = (int)std::min<long long>((t.n_partial + threads - 1) / threads, 148 * 8);
-    hint_tc3_reduce_kernel<<<blocks, threads, 0, st>>>(d.part_dst, partials, grid, (long long)t.n_partial, dparams);
+    hint_tc3_reduce_kernel<<<blocks, threads, 0, st>>>(d.part_dst, partials, grid, (long long)t.n_partial, dparams); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -92,7 +101,7 @@ cudaError_t tc3_debug_run(const T3Plan& t, const DevTc3& d, int n_epi_limit, con
     while (nm < (int)t.mmas.size() && nm > 0 && !(t.mmas[nm - 1].flags & T3M_SS) && !(t.mmas[nm - 1].flags & T3M_ENDCHUNK)) ++nm;
     P.n_mma = nm; P.n_epi = n_epi_limit; P.n_chunks = nch;
     hint_tc3_bwd_kernel<<<1, kT3Threads, t.smem_bytes, st>>>(P, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials,
-                                                             (long long)t.n_partial, std::min<long long>(B, 128), dump, nullptr);
+                                                             (long long)t.n_partial, std::min<long long>(B, 128), dump, nullptr); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 

@@ -25,7 +25,7 @@ int tc3_bwd_ctas(const DevTc3& d, long long B);
 // fused backward + deterministic reduction of the per-CTA partial gradients into dparams
 cudaError_t tc3_launch_bwd(const T3Plan& t, const DevTc3& d, int grid, const float* z, const float* cond, const float* packed,
                            const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc, float* partials,
-                           float* dparams, long long B, cudaStream_t st, long long* prof = nullptr);
+                           float* dparams, long long B, cudaStream_t st, long long* prof = nullptr, float nll_scale = 0.f);
 
 // developer aid: one tile, stop after n_epi_limit epilogue steps, dump TMEM [128][512] + raw shared memory (floats)
 cudaError_t tc3_debug_run(const T3Plan& t, const DevTc3& d, int n_epi_limit, const float* z, const float* cond, const float* packed,

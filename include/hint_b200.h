@@ -110,9 +110,38 @@ int hint_backward(const hint_plan_t* plan, const float* z, const float* c, const
                   const float* dz, const float* dlogdet, int64_t B, int32_t mode, float* x_rec, float* dx,
                   float* dc, float* dparams, void* workspace, size_t workspace_bytes, void* stream);
 
+/* --- training edge: the step around the blocks as this library's own kernels ------------------------
+ * hint_backward_nll: hint_backward for the blocks of a flow trained with the reference's NLL loss
+ * (train_unconditional.py:128-132: L = 0.5*mean_b|z_b|^2 - mean_b sum_blocks logdet_b).  dlogdet is never read from memory
+ * (it is -grad_scale for every block, grad_scale = 1/B_global); for the LAST block pass dz = NULL: dz = grad_scale * z is
+ * generated in the kernel's tile load as well.  Earlier blocks pass the dx of the block after them as dz.
+ * Implemented by the register-chained and tcgen05 training kernels (HINT_MODE_TF32 / _CHAIN / _TC3); other modes return
+ * HINT_ERR_UNSUPPORTED and the host materialises the gradients itself. */
+int hint_backward_nll(const hint_plan_t* plan, const float* z, const float* c, const float* params, const float* dz,
+                      float grad_scale, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* out[i] = x[i] + sigma * N(0,1), i < n: replaces `x += noise * torch.randn_like(x)` (train_unconditional.py:121-123).
+ * Counter-based Philox4x32-10 + Box-Muller: (seed, offset) identify the stream, element i owns counter i/4; out may alias x. */
+int hint_add_noise(const float* x, float* out, int64_t n, float sigma, uint64_t seed, uint64_t offset, void* stream);
+/* loss3[0] = 0.5*mean_b|z_b|^2 - mean_b logdet_b, loss3[1], loss3[2] = the two terms (device floats); logdet = the sum of the
+ * n_logdets (1..64) per-block [B] vectors whose device pointers the HOST array `logdets` holds (the per-block log-dets of a
+ * flow are summed inside the reduction).  Deterministic two-stage fp64 reduction.  Replaces train_unconditional.py:128-132. */
+size_t hint_nll_workspace_bytes(void);
+int hint_nll_loss(const float* z, const float* const* logdets, int32_t n_logdets, int64_t B, int32_t d, float* loss3,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* One optimizer step over n_tensors flat fp32 tensors in ONE launch: g = clamp(grad, +-grad_clamp) (skipped when
+ * grad_clamp <= 0), then torch.optim.Adam's update with L2 weight decay and bias correction for step number `step` >= 1.
+ * Replaces train_unconditional.py:141-144 with the optimizer of :174-176.  The pointer arrays live on the host. */
+int hint_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_clamp, int64_t step, void* stream);
+
 const char* hint_last_error(void);
 /* "hint_b200 <version> sm_100a" — lets the host check it loaded the in-tree build */
 const char* hint_version(void);
+/* number of CUDA kernels this library has launched in this process so far (all streams; monotone).  A host that wants to
+ * report how many of the library's kernels ran inside a timed region takes the difference of two reads. */
+uint64_t hint_launch_count(void);
 
 #ifdef __cplusplus
 }

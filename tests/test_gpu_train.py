@@ -1,0 +1,158 @@
+"""GPU tests of the training edge (train_unconditional.py:121-144,174-176) through the C ABI:
+hint_add_noise, hint_nll_loss, hint_backward_nll, hint_adam_step, hint_launch_count and the autograd-free FusedTrainStep
+built from them.  Oracles: torch (fp64 where it matters) for the elementwise / reduction kernels, the library's own
+hint_backward with a materialised loss gradient for the fused NLL gradient, and the reference-surface step
+(module forward + loss.backward() + clamp_ + torch.optim.Adam) for the whole step."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ADAM = dict(lr=0.01, betas=(0.9, 0.95), eps=1e-4, weight_decay=1.86e-5)   # configs/uci_data/miniboone_hint_8.py:38-44
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def test_fused_clamp_adam_matches_torch(dev):
+    """Tolerance 2e-6 relative to max|p| after 5 steps: same formula as torch.optim.Adam, different fp32 association."""
+    from hint_b200 import FusedClampAdam
+    g = torch.Generator().manual_seed(0)
+    sizes = [1, 3, 4, 1021, 4096, 31598]
+    ps_a = [torch.randn(n, generator=g).to(dev).requires_grad_(True) for n in sizes]
+    ps_b = [p.detach().clone().requires_grad_(True) for p in ps_a]
+    opt_a = FusedClampAdam(ps_a, grad_clamp=5.0, **ADAM)
+    opt_b = torch.optim.Adam(ps_b, **ADAM)
+    for step in range(5):
+        for pa, pb in zip(ps_a, ps_b):
+            gr = (10.0 * torch.randn(pa.shape, generator=g)).to(dev)   # |g| > 5 occurs: the clamp matters
+            pa.grad = gr.clone()
+            pb.grad = gr.clone().clamp_(-5.0, 5.0)
+        opt_a.step()
+        opt_b.step()
+    for pa, pb in zip(ps_a, ps_b):
+        assert float((pa - pb).detach().abs().max()) <= 2e-6 * max(1.0, float(pb.detach().abs().max()))
+    assert opt_a.state[ps_a[0]]["step"] == 5
+
+
+def test_adam_rejects_cpu_tensors():
+    from hint_b200 import FusedClampAdam
+    p = torch.zeros(4, requires_grad=True)
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        FusedClampAdam([p]).step()
+
+
+@pytest.mark.parametrize("B,d,nj", [(1, 1, 1), (77, 43, 3), (4096, 6, 8), (100000, 43, 1)])
+def test_nll_loss_matches_fp64(dev, B, d, nj):
+    from hint_b200 import nll_loss_fused
+    g = torch.Generator().manual_seed(B)
+    z = torch.randn(B, d, generator=g)
+    js = [torch.randn(B, generator=g) for _ in range(nj)]
+    ref0 = 0.5 * (z.double() ** 2).sum(1).mean()
+    ref1 = sum(j.double() for j in js).mean()
+    out = nll_loss_fused(z.to(dev), [j.to(dev) for j in js]).cpu().double()
+    assert abs(float(out[1] - ref0)) <= 1e-6 * max(1.0, abs(float(ref0)))
+    assert abs(float(out[2] - ref1)) <= 1e-6 * max(1.0, abs(float(ref1)))
+    assert abs(float(out[0] - (ref0 - ref1))) <= 2e-6 * max(1.0, abs(float(ref0)), abs(float(ref1)))
+
+
+def test_noise_is_standard_normal_and_counter_based(dev):
+    from hint_b200 import add_noise
+    x = torch.zeros(1 << 20, 3, device=dev)[:-1]   # numel not a multiple of 4: exercises the tail
+    a = add_noise(x, 1.0, seed=7, offset=0)
+    b = add_noise(x, 1.0, seed=7, offset=0)
+    c = add_noise(x, 1.0, seed=7, offset=1)
+    d = add_noise(x, 1.0, seed=8, offset=0)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    v = a.double().flatten()
+    n = v.numel()
+    assert abs(float(v.mean())) < 5.0 / np.sqrt(n) and abs(float(v.std()) - 1.0) < 5.0 / np.sqrt(2 * n)
+    assert abs(float((v ** 3).mean())) < 0.02 and abs(float((v ** 4).mean()) - 3.0) < 0.05   # skewness 0, kurtosis 3
+    assert abs(float((v[:-1] * v[1:]).mean())) < 5.0 / np.sqrt(n)                              # neighbours uncorrelated
+    assert float(a.abs().max()) < 7.0 and torch.isfinite(a).all()
+    y = torch.randn(1000, 43, device=dev)
+    out = add_noise(y, 0.01, seed=1)
+    assert 0.008 < float((out - y).std()) < 0.012
+
+
+CONFIGS = [("d43_chain", 43, 0, [67, 33, 16, 8], "tf32"), ("lens_cond_chain", 20, 2, [68, 34, 17, 17], "tf32"),
+           ("gas_tc3", 8, 0, [128, 64, 32, 16], "tf32"), ("power_tc3", 6, 0, [140, 70, 35, 17], "tf32_tc3"),
+           ("gas_fp32_materialised", 8, 0, [128, 64, 32, 16], "fp32")]
+
+
+@pytest.mark.parametrize("name,d,dc,ci,mode", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_backward_nll_equals_backward_with_materialised_gradient(dev, name, d, dc, ci, mode):
+    """The loss gradient generated in the tile load (dz = z/B, dlogdet = -1/B) is the same fp32 product torch computes, and the
+    kernels are deterministic: results agree to a few ulp (the tcgen05 kernel accumulates its partials with RED, ordered).
+    Ragged batch (several tiles, partial last tile)."""
+    from hint_b200.block import TreePlan
+    tp = TreePlan(d, dc, ci, 4.0, -1, 2, False)
+    B = 128 * 5 + 37
+    g = torch.Generator().manual_seed(3)
+    flat = (0.05 * torch.randn(tp.n_params, generator=g)).to(dev)
+    z = torch.randn(B, d, generator=g).to(dev)
+    c = torch.randn(B, dc, generator=g).to(dev) if dc else None
+    s = 1.0 / B
+    dx0, dc0, dp0, _ = tp.backward(z, c, flat, z * s, torch.full((B,), -s, device=dev), mode=mode)
+    dx1, dc1, dp1, _ = tp.backward(z, c, flat, None, None, mode=mode, nll_scale=s)
+    tol = lambda ref: 1e-6 * max(1e-30, float(ref.abs().max()))
+    assert float((dx1 - dx0).abs().max()) <= tol(dx0) and float((dp1 - dp0).abs().max()) <= tol(dp0)
+    if dc:
+        assert float((dc1 - dc0).abs().max()) <= tol(dc0)
+    # earlier blocks: dz from memory, dlogdet generated
+    up = torch.randn(B, d, generator=g).to(dev) * s
+    dx2, _, dp2, _ = tp.backward(z, c, flat, up, torch.full((B,), -s, device=dev), mode=mode)
+    dx3, _, dp3, _ = tp.backward(z, c, flat, up, None, mode=mode, nll_scale=s)
+    assert float((dx3 - dx2).abs().max()) <= tol(dx2) and float((dp3 - dp2).abs().max()) <= tol(dp2)
+
+
+@pytest.mark.parametrize("wl", [dict(d=43, ci=[67, 33, 16, 8], nb=3, mode="tf32"), dict(d=8, ci=[128, 64, 32, 16], nb=2, mode="tf32"),
+                                dict(d=20, ci=[68, 34, 17, 17], nb=2, mode="fp32")], ids=["d43_tf32", "gas_tf32", "lens_fp32"])
+def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
+    """Steps without noise against module forward + nll_loss + backward + clamp_ + torch.optim.Adam.  After ONE step the
+    parameters agree to 2e-6 * max|p| in every mode (same kernels, same inputs; only Adam's fp32 association differs).  After
+    three steps the bound is 1e-5 in fp32 and 5e-3 in tf32: a last-bit difference of a weight can flip its 10-bit tf32 rounding,
+    which changes that product by 1e-3 relative and Adam's normalised update m/sqrt(v) carries it into the next step."""
+    import hint_b200
+    from hint_b200 import HintFlow, nll_loss, FusedClampAdam, FusedTrainStep
+    old = hint_b200.get_precision()
+    hint_b200.set_precision(wl["mode"])
+    try:
+        torch.manual_seed(0)
+        ma = HintFlow(wl["d"], wl["nb"], wl["ci"]).to(dev).init_like_reference_scripts(0.05)
+        mb = HintFlow(wl["d"], wl["nb"], wl["ci"]).to(dev)
+        mb.load_state_dict(ma.state_dict())
+        B = 1000
+        x = torch.randn(B, wl["d"], device=dev)
+        opt_a = FusedClampAdam(list(ma.parameters()), grad_clamp=5.0, **ADAM)
+        tr = FusedTrainStep(ma, opt_a, noise=0.0)
+        opt_b = torch.optim.Adam(mb.parameters(), **ADAM)
+        n0 = hint_b200._lib.load().hint_launch_count()
+        for it in range(3):
+            la = tr.step(x)
+            opt_b.zero_grad()
+            z, J = mb(x)
+            lb = nll_loss(z, J)
+            lb.backward()
+            for p in mb.parameters():
+                p.grad.clamp_(-5.0, 5.0)
+            opt_b.step()
+            assert abs(float(la[0]) - float(lb)) <= 1e-4 * max(1.0, abs(float(lb)))
+            tol = 2e-6 if it == 0 else (1e-5 if wl["mode"] == "fp32" else 5e-3)
+            with torch.no_grad():
+                for pa, pb in zip(ma.parameters(), mb.parameters()):
+                    assert float((pa - pb).abs().max()) <= tol * float(pb.abs().max()), (it, float((pa - pb).abs().max()))
+        assert hint_b200._lib.load().hint_launch_count() > n0
+        # and the loss goes down
+        l0 = float(tr.step(x)[0])
+        for _ in range(20):
+            l1 = float(tr.step(x)[0])
+        assert l1 < l0
+    finally:
+        hint_b200.set_precision(old)
