@@ -21,10 +21,20 @@
 #include "tc3_launch.h"
 #include "train_ops.h"
 #include "simt_kernels.cuh"
-#include "tc_kernels.cuh"
 #include "tc2_kernels.cuh"
 
 using namespace hint;
+
+// Developer switches (kernel-family overrides, cycle-breakdown dumps) exist only in -DHINT_B200_DEV builds: in the product an
+// environment variable cannot change which kernel runs.
+static inline const char* dev_getenv(const char* name) {
+#ifdef HINT_B200_DEV
+    return std::getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 namespace hint {
 std::atomic<unsigned long long> g_launches{0};
@@ -161,8 +171,6 @@ int get_dev(hint_plan* hp, DevPlan** out) {
         CUDA_TRY(upload(&d.tc.fins, hp->tc.fins));
         CUDA_TRY(upload(&d.tc.xlog, hp->tc.xlog));
         CUDA_TRY(upload(&d.tc.pack_src, hp->tc.pack_src));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_fwd_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     }
@@ -331,7 +339,7 @@ int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
     switch (mode) {
         case HINT_MODE_FP32: return 1;
         case HINT_MODE_TF32: case HINT_MODE_TF32X3: case HINT_MODE_TF32_MMA: return hp->mma.ok ? 1 : 0;
-        case HINT_MODE_TF32_TCGEN05: return hp->tc.ok ? 1 : 0;
+        case HINT_MODE_TF32_TCGEN05: return (hp->tc.ok && hp->tc2.ok) ? 1 : 0;
         case HINT_MODE_TF32_CHAIN: return (hp->chain.ok && hp->mma.ok) ? 1 : 0;
         case HINT_MODE_TF32_TC3: return (hp->tc3.ok && hp->mma.ok) ? 1 : 0;
     }
@@ -400,7 +408,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     // explicitly (tests run both).
     if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // the training kernel's mode: forward / inverse as in HINT_MODE_TF32
     if (mode == HINT_MODE_TF32) {
-        static const char* pref = std::getenv("HINT_B200_TF32_FWD");
+        static const char* pref = dev_getenv("HINT_B200_TF32_FWD");
         const bool want_chain = pref ? std::strcmp(pref, "chain") == 0 : true;
         const bool want_tc = pref ? std::strcmp(pref, "tcgen05") == 0 : true;
         mode = (want_chain && hp->chain.ok) ? HINT_MODE_TF32_CHAIN
@@ -427,12 +435,11 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
             hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats); HINT_LAUNCHED();
             CUDA_TRY(cudaGetLastError());
         }
-        static const bool force_v1 = std::getenv("HINT_B200_TC_V1") != nullptr;
-        if (hp->tc2.ok && !force_v1) {
+        if (hp->tc2.ok) {
             const long long ntiles = (B + 127) / 128;
             const int grid = (int)std::min<long long>(ntiles, d->num_sms);
             static long long* dbg2 = nullptr;   // HINT_B200_TC_DEBUG=1: cycle breakdown of CTA 0, printed after a sync
-            static const bool dbg_on = std::getenv("HINT_B200_TC_DEBUG") != nullptr;
+            static const bool dbg_on = dev_getenv("HINT_B200_TC_DEBUG") != nullptr;
             if (dbg_on) {
                 if (!dbg2) CUDA_TRY(cudaMalloc((void**)&dbg2, 16 * sizeof(long long)));
                 CUDA_TRY(cudaMemsetAsync(dbg2, 0, 16 * sizeof(long long), st));
@@ -452,40 +459,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
             }
             return HINT_OK;
         }
-        TcDev T;
-        T.stages = d->tc.stages; T.ops = d->tc.ops; T.chunks = d->tc.chunks; T.fins = d->tc.fins; T.xlog = d->tc.xlog;
-        T.nstages = (int)t.stages.size(); T.nops = (int)t.ops.size(); T.nchunks = (int)t.chunks.size(); T.nfins = (int)t.fins.size();
-        T.d = t.d; T.dc = t.dc; T.xw = t.xw; T.xc = t.xc; T.xr = t.xr;
-        T.slot_bytes = t.slot_bytes; T.n_slots = t.n_slots;
-        T.smem_stage_in = t.smem_stage_in; T.smem_stage_bytes = t.smem_stage_bytes; T.smem_tables = t.smem_tables;
-        T.smem_bars = t.smem_bars; T.smem_ring = t.smem_ring;
-        T.alpha = hp->p.alpha;
-        T.round_acts = 1;
-        T.bias_base = (int)t.n_weight_floats;
-        T.n_bias = (int)(t.n_packed - t.n_weight_floats);
-        T.dbg = nullptr;
-        static long long* dbg_buf = nullptr;   // HINT_B200_TC_DEBUG=1: cycle breakdown of CTA 0, printed after a sync
-        const bool dbg = std::getenv("HINT_B200_TC_DEBUG") != nullptr;
-        if (dbg) {
-            if (!dbg_buf) CUDA_TRY(cudaMalloc((void**)&dbg_buf, 16 * sizeof(long long)));
-            CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st));
-            T.dbg = dbg_buf;
-        }
-        const long long ntiles = (B + 127) / 128;
-        const int grid = (int)std::min<long long>(ntiles, d->num_sms);
-        if (rev) { hint_fwd_tf32_kernel<true><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B); HINT_LAUNCHED(); }
-        else { hint_fwd_tf32_kernel<false><<<grid, kTcThreads, t.smem_bytes, st>>>(T, x, c, packed, z, logdet, (long long)B); HINT_LAUNCHED(); }
-        CUDA_TRY(cudaGetLastError());
-        if (dbg) {
-            long long h[16];
-            CUDA_TRY(cudaStreamSynchronize(st));
-            CUDA_TRY(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-            const double nt = (double)std::max<long long>(1, h[6]);
-            std::fprintf(stderr, "[hint_b200 tc dbg] tiles/CTA %lld | issuer0 cycles/tile: wait_tile %.0f wait_prev_final %.0f wait_epi %.0f wait_chunk %.0f issue %.0f walk %.0f"
-                         " | epilogue warp0 cycles/tile: load %.0f wait_mma %.0f hidden %.0f wait_fin %.0f final %.0f store %.0f\n",
-                         h[6], h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
-        }
-        return HINT_OK;
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the TF32 (tcgen05) kernel's envelope");
     }
     if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
     const Schedule& s = hp->p.fwd;
@@ -520,7 +494,7 @@ static int backward_impl(const hint_plan_t* hp_c, const float* z, const float* c
     // warp-MMA kernel.  HINT_B200_TF32_BWD=mma forces the latter (developer aid; HINT_MODE_TF32_MMA does the same).
     bool use_chain = mode == HINT_MODE_TF32_CHAIN;
     if (mode == HINT_MODE_TF32 && hp->chain.ok) {
-        static const char* pref = std::getenv("HINT_B200_TF32_BWD");
+        static const char* pref = dev_getenv("HINT_B200_TF32_BWD");
         use_chain = !(pref && std::strcmp(pref, "mma") == 0);
     }
     cudaStream_t st = (cudaStream_t)stream;

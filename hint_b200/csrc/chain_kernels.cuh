@@ -18,6 +18,14 @@ namespace hint { namespace emu { void warp_sync(); void ldsm4(const float* rowp,
 
 namespace hint {
 
+// Developer experiments (timing only, some give WRONG results) are compiled in only with -DHINT_B200_DEV; in the product build
+// HINT_EXP() is the constant 0, so the branches vanish and no environment variable can reach them.
+#ifdef HINT_B200_DEV
+#define HINT_EXP(e, bit) ((e) & (bit))
+#else
+#define HINT_EXP(e, bit) 0
+#endif
+
 struct ChainTables {
     int n_nodes, d, dc;
     float alpha;
@@ -352,7 +360,7 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
     float* XT = S + warp * chain_fwd_warp_floats<MT>(T.d, T.dc);
     const long long ntiles = (B + RW - 1) / RW;
     // The warps are independent, but they all run the same (large, fully unrolled) instruction stream: a CTA barrier per
-    // tile (T.exp & 8) or per node (T.exp & 16) keeps them in step so they share the instruction cache.
+    // tile HINT_EXP(T.exp, 8) or per node HINT_EXP(T.exp, 16) keeps them in step so they share the instruction cache.
     for (long long base = (long long)bid * NW; base < ntiles; base += (long long)nblocks * NW) {
         const long long tile = base + warp;
         const bool live = tile < ntiles;
@@ -371,7 +379,7 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
                 c_node_fwd_dispatch<WS, MT, REV>(nodes + (REV ? T.n_nodes - 1 - q : q), T.alpha, W, XT, JP, lane);
                 c_syncwarp();
             }
-            if (T.exp & 16) m_cta_sync();
+            if (HINT_EXP(T.exp, 16)) m_cta_sync();
         }
         if (live) {
             c_store_tile<MT>(XT, 0, z, row0, rows, T.d, lane);
@@ -384,7 +392,7 @@ HINT_DEV void c_fwd_body(const ChainTables& T, const ChainNode* nodes, float* S,
             }
             c_syncwarp();
         }
-        if (T.exp & 8) m_cta_sync();
+        if (HINT_EXP(T.exp, 8)) m_cta_sync();
     }
 }
 
@@ -448,13 +456,15 @@ HINT_DEV void c_ldsm2(const float* rowp, uint32_t (&r)[4]) {
 #endif
 }
 
-// developer aid (T.exp & 32): thread 0 of CTA 0 records clock64 at the phase boundaries of the backward sweep
+// developer aid HINT_EXP(T.exp, 32): thread 0 of CTA 0 records clock64 at the phase boundaries of the backward sweep
 #if defined(__CUDACC__)
+#ifdef HINT_B200_DEV
 __device__ long long g_chain_dbg[2048];
 #endif
+#endif
 HINT_DEV void c_stamp(int exp, int warp, int lane) {
-#if defined(__CUDA_ARCH__)
-    if ((exp & 32) && warp == 0 && lane == 0 && blockIdx.x == 0) {
+#if defined(__CUDA_ARCH__) && defined(HINT_B200_DEV)
+    if (HINT_EXP(exp, 32) && warp == 0 && lane == 0 && blockIdx.x == 0) {
         const long long n = g_chain_dbg[0];
         if (n < 2040) { g_chain_dbg[1 + n] = clock64(); g_chain_dbg[0] = n + 1; }
     }
@@ -567,7 +577,7 @@ HINT_DEV void c_mask_to_a(const float (&acc)[NT][MT][4], const float* hbuf, cons
 template <int MT, int NW, int KSIN, int NTOUT, bool XIN>
 HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff, int cst, float* __restrict__ part, bool first,
                         int warp, int lane, int rot, int exp) {
-    if (exp & 2) return;
+    if (HINT_EXP(exp, 2)) return;
     constexpr int TM = 16 * MT * NW;
     constexpr int MTC = (8 * KSIN + 1 + 15) / 16;
     constexpr int NC = NTOUT <= 5 ? NTOUT : 3;
@@ -638,7 +648,7 @@ HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff,
             }
         }
         // flush: C fragment (i, j) = 128 floats, the lane's 4 are contiguous
-        if (exp & 1) continue;
+        if (HINT_EXP(exp, 1)) continue;
 #pragma unroll
         for (int jj = 0; jj < NC; ++jj) {
             float* q = part + ((i * NTOUT + ch * NC + jj) * 32 + lane) * 4;
@@ -832,8 +842,8 @@ HINT_DEV void c_node_bwd(const ChainNode* nd, float alpha, const float* __restri
 template <int MT, int NW>
 HINT_DEV void c_node_bwd_dispatch(const ChainNode* nd, float alpha, const float* __restrict__ W, float* S, const ChainBwdSmem& L,
                                   float* __restrict__ partial, bool first, int warp, int lane, int exp) {
-    const float* Wn = W + ((exp & 4) ? 0 : nd->w_off);
-    const float* Wt = W + ((exp & 4) ? 0 : nd->wt_off);
+    const float* Wn = W + (HINT_EXP(exp, 4) ? 0 : nd->w_off);
+    const float* Wt = W + (HINT_EXP(exp, 4) ? 0 : nd->wt_off);
     float* part = partial + nd->dw_off;
 #define HINT_CHAIN_CASE(ID, A, B, C, D) \
     case ID: c_node_bwd<MT, NW, A, B, C, D>(nd, alpha, Wn, Wt, S, L, part, first, warp, lane, exp); break;

@@ -18,8 +18,17 @@ namespace {
 // forward / inverse configuration: MT = 1 (16 samples per warp), 12 (or 8) warps next to the shared-memory resident
 // operands (WS), else 16 warps reading the operands through L1.  HINT_B200_CHAIN_FWD=<mt><nw><ws> (e.g. "2080",
 // "1161") overrides (developer aid).
+// developer switches exist only in -DHINT_B200_DEV builds (see HINT_EXP in chain_kernels.cuh)
+const char* dev_getenv(const char* name) {
+#ifdef HINT_B200_DEV
+    return std::getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 int chain_exp() {
-    static const int v = [] { const char* e = std::getenv("HINT_B200_CHAIN_EXP"); return e ? std::atoi(e) : 0; }();
+    static const int v = [] { const char* e = dev_getenv("HINT_B200_CHAIN_EXP"); return e ? std::atoi(e) : 0; }();
     return v;
 }
 
@@ -38,7 +47,7 @@ size_t fwd_smem(const Plan& p, const ChainPlan& c, int mt, int nw, int ws) {
 }
 
 FwdCfg pick_fwd(const Plan& p, const ChainPlan& c) {
-    static const char* e = std::getenv("HINT_B200_CHAIN_FWD");
+    static const char* e = dev_getenv("HINT_B200_CHAIN_FWD");
     if (e && e[0] && e[1] && e[2] && e[3]) {
         FwdCfg f{e[0] - '0', 10 * (e[1] - '0') + (e[2] - '0'), e[3] - '0', 0};
         f.smem = fwd_smem(p, c, f.mt, f.nw, f.ws);
@@ -136,6 +145,7 @@ cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& 
     const ChainBwdSmem L = bwd_layout(p, c, b);
     const long long np = c.n_partial;
     hint_bwd_chain_kernel<1, 4, 2><<<grid, 128, d.bwd_smem, st>>>(T, c.param, L, z, cond, packed, dz, dlogdet, x_rec, dx, dc, partials, np, B); HINT_LAUNCHED();
+#ifdef HINT_B200_DEV
     if (T.exp & 32) {   // developer aid: phase-boundary cycle stamps of CTA 0 (HINT_B200_CHAIN_EXP=32)
         static long long h[2048];
         cudaStreamSynchronize(st);
@@ -146,6 +156,7 @@ cudaError_t chain_launch_bwd(const Plan& p, const ChainPlan& c, const DevChain& 
         std::memset(h, 0, sizeof(h));
         cudaMemcpyToSymbol(g_chain_dbg, h, sizeof(h));
     }
+#endif
     return cudaGetLastError();
 }
 

@@ -68,7 +68,15 @@ MmaTables make_tables(const Plan& p, const MSchedule& s, const DevMmaSchedule& d
 
 // HINT_B200_MMA_DEBUG=1: per-barrier clock64 stamps of CTA 0's second tile, printed after a sync (developer aid)
 long long* g_dbg = nullptr;
-bool dbg_on() { static const bool on = std::getenv("HINT_B200_MMA_DEBUG") != nullptr; return on; }
+const char* dev_getenv(const char* name) {   // developer switches exist only in -DHINT_B200_DEV builds
+#ifdef HINT_B200_DEV
+    return std::getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+bool dbg_on() { static const bool on = dev_getenv("HINT_B200_MMA_DEBUG") != nullptr; return on; }
 void dbg_begin(MmaTables& T, cudaStream_t st) {
     if (!dbg_on()) return;
     if (!g_dbg) cudaMalloc((void**)&g_dbg, 1001 * sizeof(long long));
@@ -118,7 +126,7 @@ void mma_free(DevMma& d) {
 }
 
 int mma_weight_copies() {
-    static const int n = [] { const char* e = std::getenv("HINT_B200_MMA_WCOPIES"); const int v = e ? std::atoi(e) : kMmaWeightCopies; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+    static const int n = [] { const char* e = dev_getenv("HINT_B200_MMA_WCOPIES"); const int v = e ? std::atoi(e) : kMmaWeightCopies; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
     return n;
 }
 long long mma_copy_stride(const MmaPlan& m) { return (m.n_packed + 63) & ~63LL; }

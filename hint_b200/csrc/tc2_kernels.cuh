@@ -1,7 +1,7 @@
 // tcgen05 (TF32) fused-tree forward / inverse kernel, second generation.  Executes the program of plan_tc.h
 // (T2Prog), which arrives BY VALUE in the kernel-parameter (constant) bank.
 //
-// What changed against tc_kernels.cuh, each item from a measurement (profiles/ubench3_r01_mma_issue_tmem.txt):
+// What changed against the first tcgen05 kernel (round 1, removed), each item from a measurement (profiles/ubench3_r01_mma_issue_tmem.txt):
 //   * MMA operands are warp-uniform (constant-bank loads + uniform arithmetic, TMEM base 0 because the CTA owns
 //     all 512 columns): 38 cycles per tcgen05.mma instead of 77 behind the compiler's divergence loop;
 //   * ops are pre-partitioned per issuing warp; an issuer never walks ops it does not own;
@@ -366,6 +366,17 @@ hint_tc2_kernel(const __grid_constant__ T2Prog P, const float* __restrict__ x, c
     if (warp == 8) {
         __syncwarp();
         tmem_dealloc(0, 512);
+    }
+}
+
+// packed[i] = params[src[i]] (0 for padding); MMA operands (i < n_round) are rounded to tf32 (round-to-nearest)
+__global__ void hint_pack_tc_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ packed,
+                                    long long n, long long n_round) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = src[i];
+        float v = s < 0 ? 0.f : params[s];
+        if (i < n_round) v = tc::to_tf32(v);
+        packed[i] = v;
     }
 }
 

@@ -66,7 +66,28 @@ CONFIGS = [
     ("lens_hint_8_full", 20, 0, [68, 34, 17, 17], -1, 2500),
     ("lens_concat_cond", 20, 2, [68, 34, 17, 17], -1, 1000),
     ("gas_like", 8, 0, [64, 32, 16, 8], -1, 4097),
+    # the BASELINE configs' REAL widths: wide single nodes, second M tile, ragged K
+    ("power_hint_8", 6, 0, [140, 70, 35, 17], -1, 1660),
+    ("gas_hint_8", 8, 0, [128, 64, 32, 16], -1, 853),
+    ("miniboone_hint_4", 42, 0, [102, 51, 25, 12], -1, 300),
+    ("plus_hint_4_3", 100, 0, [314, 157, 78, 39], 3, 500),
+    ("plus_hint_4_full", 100, 0, [263, 131, 65, 32, 32], -1, 300),
+    ("plus_cond_recursive_4", 100, 4, [267, 133, 66], -1, 300),
 ]
+
+
+def _report(tag, **errs):
+    """Measured errors go to stdout (pytest -s / the captured log) and to gpurun_out/tf32_errors.txt on the GPU box."""
+    line = tag + "  " + "  ".join(f"{k} {v:.2e}" for k, v in errs.items())
+    print(line)
+    try:
+        import os
+        from conftest import ROOT
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "tf32_errors.txt"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
 
 
 @pytest.mark.parametrize("mode", ["tf32", "tf32_chain", "tf32_mma", "tf32_tcgen05"])
@@ -92,6 +113,7 @@ def test_reference_configs_tf32(cfg, mode):
             pytest.skip(str(e))
         z32, J32 = blk.plan.forward(x.to(dev), cg, blk.flat.detach(), mode="fp32")
         xr, Jr = blk.plan.forward(z, cg, blk.flat.detach(), rev=True, mode=mode)
+    _report(f"fwd {name:22s} {mode:13s} kaiming", z=_err(z, z_ref.numpy()), J=_err(J, J_ref.numpy()), xrec=_err(xr, x.double().numpy()))
     assert _err(z, z_ref.numpy()) < TF32_TOL and _err(J, J_ref.numpy()) < TF32_TOL
     assert _err(z32, z_ref.numpy()) < 1e-5
     assert _err(xr, x.double().numpy()) < TF32_TOL * max(1.0, float(z_ref.abs().max()))
@@ -136,15 +158,19 @@ def test_golden_3xtf32_full_parity(golden):
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c[0])
-@pytest.mark.parametrize("mode,tol", [("tf32", 2e-2), ("tf32x3", 2e-4)])
+@pytest.mark.parametrize("mode,tol", [("tf32", 2e-2), ("tf32_mma", 2e-2), ("tf32_tc3", 2e-2), ("tf32x3", 2e-4)])
 def test_backward_tensor_core_modes(cfg, mode, tol):
-    """Backward of the warp-MMA kernels against the fp64 oracle on the reference configs (relative L2 error of dx, dc and the
-    flat parameter gradient; single-pass TF32 bound 2e-2: ReLU kinks make a few samples flip, see test_gpu_parity.py)."""
+    """Backward of every tensor-core kernel family (tf32 = the default dispatch: register-chained / tcgen05 training kernel /
+    interpreter) against the fp64 oracle on the reference configs' real widths (relative L2 error of dx, dc and the flat
+    parameter gradient; single-pass TF32 bound 2e-2 on Kaiming-scale weights: ReLU kinks make a few samples flip, see
+    test_gpu_parity.py)."""
     name, d, dc, ci, ms, B = cfg
     from hint_b200 import HierarchicalAffineCouplingBlock
     dev = torch.device("cuda:0")
     torch.manual_seed(99)
     blk = HierarchicalAffineCouplingBlock([(d,)], dims_c=[(dc,)] if dc else [], c_internal=list(ci), max_splits=ms)
+    if not blk.plan.mode_supported(mode):
+        pytest.skip(f"{name} is outside the {mode} envelope")
     with torch.no_grad():
         blk.flat.mul_(0.7)
     flat64 = blk.flat.detach().double().clone()
@@ -161,8 +187,10 @@ def test_backward_tensor_core_modes(cfg, mode, tol):
     with torch.no_grad():
         dx, dcc, dflat, xrec = blk.plan.backward(z_ref.float().to(dev), cg, blk.flat.detach(), dz.float().to(dev),
                                                  dJ.float().to(dev), mode=mode, want_xrec=True)
+    _report(f"bwd {name:22s} {mode:13s} kaiming*0.7", dx=_l2(dx, dx_ref.numpy()), dparams=_l2(dflat, dflat_ref.numpy()),
+            xrec=_l2(xrec, x.double().numpy()))
     assert _l2(dx, dx_ref.numpy()) < tol and _l2(dflat, dflat_ref.numpy()) < tol
-    assert _l2(xrec, x.double().numpy()) < (5e-3 if mode == "tf32" else 1e-5)
+    assert _l2(xrec, x.double().numpy()) < (1e-5 if mode == "tf32x3" else 5e-3)
     if dc:   # dc sums the input gradients of EVERY node's subnets (hint.py:76), so it collects the most TF32 rounding noise
         assert _l2(dcc, dc_ref.numpy()) < 1.5 * tol
 
@@ -252,3 +280,86 @@ def test_random_trees_chain_against_the_oracle(seed):
             dx2, dc2, dflat2, _ = blk.plan.backward(z_ref.float().to(dev), cg, blk.flat.detach(), dz.float().to(dev), dJ.float().to(dev),
                                                     mode="tf32_mma")
         assert _l2(dx, dx2.double().cpu().numpy()) < 2e-3 and _l2(dflat, dflat2.double().cpu().numpy()) < 2e-3
+
+
+TRAINED = [
+    ("power_hint_8", 6, [140, 70, 35, 17], -1),
+    ("gas_hint_8", 8, [128, 64, 32, 16], -1),
+    ("miniboone_hint_4", 42, [102, 51, 25, 12], -1),
+    ("d43_hint_8", 43, [67, 33, 16, 8], -1),
+    ("lens_hint_8_full", 20, [68, 34, 17, 17], -1),
+    ("plus_hint_4_3", 100, [314, 157, 78, 39], 3),
+]
+
+
+@pytest.mark.parametrize("cfg", TRAINED, ids=lambda c: c[0])
+def test_briefly_trained_weights_meet_the_stated_tf32_bound(cfg):
+    """the goldens are init-scale only, so this fixture TRAINS a 2-block flow with the reference recipe
+    (train_unconditional.py:121-144: noise 0.01, NLL, clamp 5, Adam lr 0.01 / betas (0.9, 0.95) / eps 1e-4 / wd 1.86e-5, init
+    0.005*randn; 300 steps on a fixed batch of 2048 standardised GMM samples: max|w| reaches 1.3 .. 2.5) in the FP32 mode on the
+    GPU, then checks every block in the benchmarked mode `tf32` against the fp64 oracle on the activations the flow actually sees.
+
+    Stated bound of the single-pass TF32 mode on trained weights, relative to max(1, |ref|_inf):
+        z <= 5e-3 (measured 3e-4 .. 4.6e-3), log-det <= 1e-3 (measured 8e-5 .. 9.7e-4), x-reconstruction <= 1e-4,
+        gradients (relative L2) dx <= 3e-2, dparams <= 1e-2 (measured 3.6e-3 .. 2.2e-2 / 9e-4 .. 8e-3).
+    BASELINE.md section 5 suggested z <= 2e-3 from an emulation on weights with max|w| <= 1.3; this fixture trains harder and the
+    error grows with the weight scale, so the bound is restated from measurement.  That the error is the arithmetic's and not
+    the kernels' is checked against a yardstick: the same block evaluated by the oracle in float32 ON THE GPU with
+    torch.backends.cuda.matmul.allow_tf32 = True - i.e. the reference module as PyTorch itself would run it in TF32 (cuBLAS
+    truncates operands, these kernels round to nearest) - whose error against fp64 bounds ours: ours <= 1.5 x PyTorch-TF32's
+    (+ 2e-4 floor)."""
+    import hint_b200
+    from hint_b200 import HintFlow, FusedClampAdam, FusedTrainStep
+    name, d, ci, ms = cfg
+    dev = torch.device("cuda:0")
+    old = hint_b200.get_precision()
+    hint_b200.set_precision("fp32")
+    try:
+        torch.manual_seed(5)
+        model = HintFlow(d, 2, ci, max_splits=ms).to(dev).init_like_reference_scripts(0.005)
+        g = torch.Generator().manual_seed(17)
+        means, stds = 3.0 * torch.randn(8, d, generator=g), 0.3 + torch.rand(8, d, generator=g)
+        comp = torch.randint(0, 8, (2048,), generator=g)
+        x = means[comp] + stds[comp] * torch.randn(2048, d, generator=g)
+        x = ((x - x.mean(0)) / x.std(0)).to(dev)
+        opt = FusedClampAdam(list(model.parameters()), grad_clamp=5.0, lr=0.01, betas=(0.9, 0.95), eps=1e-4, weight_decay=1.86e-5)
+        tr = FusedTrainStep(model, opt, noise=0.01, seed=3)
+        l0 = float(tr.step(x)[0])
+        for _ in range(300):
+            l1 = float(tr.step(x)[0])
+        assert l1 < l0 - 0.5, (l0, l1)     # it did train
+    finally:
+        hint_b200.set_precision(old)
+    plan = O.build_plan(d, 0, ci, ms)
+    h = x[:512]
+    B = h.shape[0]
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    for bi, blk in enumerate(model.blocks):
+        flat = blk.flat.detach()
+        f64 = flat.double().cpu()
+        z_ref, J_ref = O.forward_fast(plan, f64, h.double().cpu(), None)
+        dz = z_ref / B
+        dJ = torch.full((B,), -1.0 / B, dtype=torch.float64)
+        _, dx_ref, _, dp_ref = O.backward_from_output(plan, f64, z_ref, None, dz, dJ)
+        with torch.no_grad():
+            z, J = blk.plan.forward(h, None, flat, mode="tf32")
+            xr, _ = blk.plan.forward(z, None, flat, rev=True, mode="tf32")
+            dx, _, dflat, _ = blk.plan.backward(z_ref.float().to(dev), None, flat, dz.float().to(dev), dJ.float().to(dev), mode="tf32")
+            torch.backends.cuda.matmul.allow_tf32 = True     # yardstick: PyTorch's own TF32 on the same block
+            try:
+                zt, Jt = O.forward_fast(plan, flat, h, None)
+                _, dxt, _, dpt = O.backward_from_output(plan, flat, z_ref.float().to(dev), None, dz.float().to(dev), dJ.float().to(dev))
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        ez, eJ, ex = _err(z, z_ref.numpy()), _err(J, J_ref.numpy()), _err(xr, h.double().cpu().numpy())
+        gdx, gdp = _l2(dx, dx_ref.numpy()), _l2(dflat, dp_ref.numpy())
+        tz, tJ = _err(zt, z_ref.numpy()), _err(Jt, J_ref.numpy())
+        tdx, tdp = _l2(dxt, dx_ref.numpy()), _l2(dpt, dp_ref.numpy())
+        _report(f"trained {name:18s} block {bi} max|w| {float(flat.abs().max()):.2f}", z=ez, J=eJ, xrec=ex, dx=gdx, dparams=gdp,
+                torch_tf32_z=tz, torch_tf32_J=tJ, torch_tf32_dx=tdx, torch_tf32_dparams=tdp)
+        assert ez <= 5e-3 and eJ <= 1e-3
+        assert ex <= 1e-4 * max(1.0, float(z_ref.abs().max()))
+        assert gdx <= 3e-2 and gdp <= 1e-2
+        assert ez <= 1.5 * tz + 2e-4 and eJ <= 1.5 * tJ + 2e-4
+        assert gdx <= 1.5 * tdx + 2e-3 and gdp <= 1.5 * tdp + 2e-3
+        h = z_ref.float().to(dev)

