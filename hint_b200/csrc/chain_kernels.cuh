@@ -26,6 +26,22 @@ namespace hint {
 #define HINT_EXP(e, bit) 0
 #endif
 
+// L2 residency hints.  The backward streams z / dz in and dx out once (evict-first) while the per-CTA partial-gradient buffers
+// are re-accumulated after every tile (evict-last): without the hints the streamed tiles push the 85 MB of partials out of the
+// 126 MB L2 and every flush goes to DRAM (round 1: 5.07 GB of DRAM traffic per launch for 0.55 GB of algorithmic bytes).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long c_policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long c_policy_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif
+
 struct ChainTables {
     int n_nodes, d, dc;
     float alpha;
@@ -296,7 +312,8 @@ HINT_DEV void c_load_tile(float* XT, int col_base, const float* __restrict__ gsr
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
             // streamed once: keep the tile out of L1, which holds the weights
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(src + i));
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(src + i), "l"(c_policy_evict_first()));
 #else
             for (int e = 0; e < 4; ++e) v[e] = src[i + e];
 #endif
@@ -334,7 +351,8 @@ HINT_DEV void c_store_tile(const float* XT, int col_base, float* __restrict__ gd
         if (j0 >= width) { j0 -= width; ++m0; }
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+            asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                         :: "l"(dst + i), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(c_policy_evict_first()) : "memory");
 #else
             for (int e = 0; e < 4; ++e) dst[i + e] = v[e];
 #endif
@@ -653,8 +671,11 @@ HINT_DEV void c_dw_gemm(const float* S, int aoff, const short* in_col, int boff,
         for (int jj = 0; jj < NC; ++jj) {
             float* q = part + ((i * NTOUT + ch * NC + jj) * 32 + lane) * 4;
 #if defined(__CUDA_ARCH__)
-            if (first) *reinterpret_cast<float4*>(q) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
-            else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]) : "memory");
+            const unsigned long long keep = c_policy_evict_last();
+            if (first) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                                    :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]), "l"(keep) : "memory");
+            else asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                              :: "l"(q), "f"(acc[jj][0]), "f"(acc[jj][1]), "f"(acc[jj][2]), "f"(acc[jj][3]), "l"(keep) : "memory");
 #else
             for (int e = 0; e < 4; ++e) { if (first) q[e] = acc[jj][e]; else q[e] += acc[jj][e]; }
 #endif
@@ -867,7 +888,8 @@ HINT_DEV void c_load_tile_sw(float* buf, int col_base, const float* __restrict__
         float v[4];
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(src + i));
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(src + i), "l"(c_policy_evict_first()));
 #else
             for (int e = 0; e < 4; ++e) v[e] = src[i + e];
 #endif
@@ -904,7 +926,8 @@ HINT_DEV void c_store_tile_sw(const float* buf, int col_base, float* __restrict_
         if (j0 >= width) { j0 -= width; ++m0; }
         if (i + 3 < nvalid) {
 #if defined(__CUDA_ARCH__)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+            asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                         :: "l"(dst + i), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(c_policy_evict_first()) : "memory");
 #else
             for (int e = 0; e < 4; ++e) dst[i + e] = v[e];
 #endif

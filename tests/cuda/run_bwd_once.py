@@ -1,11 +1,11 @@
-"""One tc3 backward launch per config (for ncu captures)."""
+"""One backward launch sequence per config and mode (for ncu captures): python run_bwd_once.py <cfg> <mode> <B>."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from hint_b200.block import TreePlan
 CFG = {"gas": (8, 0, [128, 64, 32, 16]), "power": (6, 0, [140, 70, 35, 17]), "d43": (43, 0, [67, 33, 16, 8]), "lens": (20, 0, [68, 34, 17, 17])}
-name = sys.argv[1] if len(sys.argv) > 1 else "gas"
-mode = sys.argv[2] if len(sys.argv) > 2 else "tf32_tc3"
-B = int(sys.argv[3]) if len(sys.argv) > 3 else 148 * 128 * 4
+name = sys.argv[1] if len(sys.argv) > 1 else "d43"
+mode = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
 d, dc, ci = CFG[name]
 dev = torch.device("cuda:0")
 tp = TreePlan(d, dc, ci, 4.0, -1, 2, False)
