@@ -76,18 +76,20 @@ class ReversibleGraphNet(nn.Module):
         self.in_nodes = [n for n in self.node_list if isinstance(n, InputNode) and not isinstance(n, ConditionNode)]
         self.cond_nodes = [n for n in self.node_list if isinstance(n, ConditionNode)]
         self.out_nodes = [n for n in self.node_list if isinstance(n, OutputNode)]
-        known = set()
-        mods = []
-        for n in self.node_list:
-            for src, _ in n.inputs:
-                assert src in known, f"node '{n.name}' is listed before its input '{src.name}'"
-            for src in n.conditions:
-                assert src in known, f"node '{n.name}' is listed before its condition '{src.name}'"
-            m = n.build_modules()
-            if m is not None:
-                mods.append(m)
-            known.add(n)
-        self.module_list = nn.ModuleList(mods)
+        # Build in dependency order: the reference's 2-lane configs list the whole y lane before the x lane, but nothing stops a
+        # config from listing a node before its condition lane, so the order is resolved here instead of being assumed.
+        built, order = set(), []
+        pending = list(self.node_list)
+        while pending:
+            progress = False
+            for n in list(pending):
+                if all(src in built for src, _ in n.inputs) and all(src in built for src in n.conditions):
+                    n.build_modules()
+                    built.add(n); order.append(n); pending.remove(n); progress = True
+            assert progress, "cyclic or dangling node references: " + ", ".join(n.name for n in pending)
+        self._order = order
+        # one entry per node, None for the input / output nodes: state_dict keys are module_list.<position in node_list>.*
+        self.module_list = nn.ModuleList([n.module for n in self.node_list])
         self._values = None
         self._rev = False
         if verbose:
@@ -110,7 +112,7 @@ class ReversibleGraphNet(nn.Module):
             assert len(xs) == len(self.in_nodes), f"expected {len(self.in_nodes)} input tensors, got {len(xs)}"
             for n, t in zip(self.in_nodes, xs):
                 vals[(n, 0)] = t
-            for n in self.node_list:
+            for n in self._order:
                 if isinstance(n, InputNode):
                     continue
                 ins = [vals[k] for k in n.inputs]
@@ -126,18 +128,21 @@ class ReversibleGraphNet(nn.Module):
             assert len(xs) == len(self.out_nodes), f"expected {len(self.out_nodes)} output tensors, got {len(xs)}"
             for n, t in zip(self.out_nodes, xs):
                 vals[n.inputs[0]] = t
-            for n in reversed(self.node_list):
-                if isinstance(n, (InputNode, OutputNode)):
-                    continue
-                outs = [vals[(n, k)] for k in range(len(n.output_dims))]
-                for cn in n.conditions:
-                    if (cn, 0) not in vals:
-                        raise NotImplementedError(f"reverse pass: the condition '{cn.name}' of node '{n.name}' is an internal node "
-                                                  "whose value is not known yet; run that lane forward and pass it explicitly")
-                kw = {"c": [vals[(cn, 0)] for cn in n.conditions]} if n.conditions else {}
-                ins = n.module(outs, rev=True, **kw)
-                for key, t in zip(n.inputs, ins):
-                    vals[key] = t
+            # A node runs backwards once all its outputs AND all its conditions are known.  A condition may be an internal node of
+            # another lane (configs/lens_shape/conditional_hint_8_full.py:78-83: the x lane is conditioned on the y lane), whose
+            # value only appears when that lane has been reversed far enough - so this is a worklist, not a fixed order.
+            pending = [n for n in reversed(self._order) if not isinstance(n, (InputNode, OutputNode))]
+            while pending:
+                progress = False
+                for n in list(pending):
+                    if all((n, k) in vals for k in range(len(n.output_dims))) and all((cn, 0) in vals for cn in n.conditions):
+                        outs = [vals[(n, k)] for k in range(len(n.output_dims))]
+                        kw = {"c": [vals[(cn, 0)] for cn in n.conditions]} if n.conditions else {}
+                        ins = n.module(outs, rev=True, **kw)
+                        for key, t in zip(n.inputs, ins):
+                            vals[key] = t
+                        pending.remove(n); progress = True
+                assert progress, "reverse pass is stuck on: " + ", ".join(n.name for n in pending)
             result = [vals[(n, 0)] for n in self.in_nodes]
         self._values, self._rev = vals, bool(rev)
         if intermediate_outputs:

@@ -57,6 +57,7 @@ class TreePlan:
                                         int(min_split_size), 1 if reshuffle else 0, ctypes.byref(handle)))
         self._h = handle
         self.d, self.dc, self.clamp = int(d), int(dc), float(clamp)
+        self.c_internal, self.max_splits, self.min_split_size = [int(v) for v in c_internal], int(max_splits), int(min_split_size)
         n = lib.hint_plan_num_nodes(handle)
         self.nodes = []
         for i in range(n):
