@@ -83,10 +83,39 @@ def test_conditions_reach_the_block_as_dims_c():
     assert blk.plan.dc == 2 and blk.dims_c == [(2,)]
 
 
-def test_baseline_couplings_fail_loudly():
-    from FrEIA.modules import AffineCoupling
-    with pytest.raises(NotImplementedError):
-        AffineCoupling([(4,)])
+def test_baseline_couplings_are_invertible_with_the_stated_jacobian():
+    """AffineCoupling / ExternalAffineCoupling / F_fully_connected (plain PyTorch, off the hot path, parity-unpinned): reverse
+    undoes forward, the cached log-det equals slogdet of the autograd Jacobian, and a two-lane graph whose x lane is
+    conditioned on an INTERNAL y-lane node reverses (configs/lens_shape/conditional_hint_8_full.py:61-102)."""
+    from FrEIA.framework import InputNode, Node, OutputNode, ReversibleGraphNet
+    from FrEIA.modules import AffineCoupling, ExternalAffineCoupling, F_fully_connected, HouseholderPerm
+    torch.manual_seed(0)
+    ac = AffineCoupling([(5,)], F_class=F_fully_connected, F_args={"internal_size": 7}).double()
+    x = torch.randn(3, 5, dtype=torch.float64)
+    y = ac([x])[0]
+    J = ac.jacobian(None)
+    assert torch.allclose(ac([y], rev=True)[0], x, atol=1e-10) and torch.allclose(ac.jacobian(None), -J)
+    jac = torch.autograd.functional.jacobian(lambda v: ac([v[None]])[0][0], x[0])
+    assert abs(float(torch.slogdet(jac)[1]) - float(J[0])) < 1e-9
+    ext = ExternalAffineCoupling([(4,)], dims_c=[(2,)], F_class=F_fully_connected, F_args={"internal_size": 6}).double()
+    c = torch.randn(3, 2, dtype=torch.float64)
+    xe = torch.randn(3, 4, dtype=torch.float64)
+    assert torch.allclose(ext([ext([xe], c=[c])[0]], c=[c], rev=True)[0], xe, atol=1e-10)
+    # two lanes, x conditioned on an internal y node; the x lane is LISTED FIRST to exercise the dependency ordering
+    yl = [InputNode(2, name="y")]
+    xl = [InputNode(4, name="x")]
+    yl.append(Node(yl[-1], HouseholderPerm, {"fixed": True, "n_reflections": 2}, name="perm_y"))
+    xl.append(Node(xl[-1], ExternalAffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": 5}}, conditions=yl[-1], name="y_to_x"))
+    yl.append(Node(yl[-1], AffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": 5}}, name="ac_y"))
+    yl.append(OutputNode(yl[-1], name="z_y"))
+    xl.append(OutputNode(xl[-1], name="z_x"))
+    net = ReversibleGraphNet([yl[0]] + xl + yl[1:], verbose=False)
+    yy, xx = torch.randn(6, 2), torch.randn(6, 4)
+    zx, zy = net([yy, xx])          # outputs in node-list order: z_x is listed before z_y here
+    y2, x2 = net([zx, zy], rev=True)
+    assert torch.allclose(y2, yy, atol=1e-5) and torch.allclose(x2, xx, atol=1e-5)
+    assert net.log_jacobian(run_forward=False).shape == (6,)
+    assert any(k.startswith("module_list.2.") for k in net.state_dict())   # keyed by the node's position in the list
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not available")
