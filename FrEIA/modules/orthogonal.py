@@ -1,7 +1,11 @@
 """``HouseholderPerm`` of the FrEIA shim: the fixed / learned orthogonal mixing the reference inserts between HINT blocks
 (configs/uci_data/miniboone_hint_8.py:60-63: ``{'fixed': True, 'n_reflections': ndim_x}``) and, with ``reshuffle=True``,
 inside the tree (hint.py:36-39).  FrEIA's source is not part of the reference, so this follows the published definition
-W = prod_i (I - 2 v_i v_i^T / |v_i|^2), forward x W, reverse x W^T, log|det| = 0  -- **parity-unpinned** (SURVEY.md 8c)."""
+W = prod_i (I - 2 v_i v_i^T / |v_i|^2), forward x W, reverse x W^T, log|det| = 0  -- **parity-unpinned** (SURVEY.md 8c).
+
+On CUDA tensors the work runs in hint_b200's own kernels (hint_householder_*: W rebuilt from the reflections in one launch per
+call when they are trainable instead of a 100-iteration Python loop, FP32 FFMA application, backward without stored
+intermediates); the plain PyTorch expressions below remain for CPU tensors - the shim's CPU tests - and define the semantics."""
 import torch
 import torch.nn as nn
 
@@ -31,6 +35,9 @@ class HouseholderPerm(nn.Module):
             self.W = self._matrix(self.Vs.detach())
 
     def forward(self, x, c=[], rev=False):
+        if x[0].is_cuda and x[0].dtype == torch.float32 and x[0].dim() == 2 and self.width <= 128:
+            from hint_b200.householder import HouseholderMix
+            return [HouseholderMix.apply(x[0], self.Vs, self.W if self.fixed else None, bool(rev))]
         W = self.W if self.fixed else self._matrix(self.Vs)
         return [x[0] @ (W.t() if rev else W)]
 

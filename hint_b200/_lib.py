@@ -20,6 +20,8 @@ EXPORTS = [
     "hint_workspace_bytes",
     "hint_forward", "hint_backward", "hint_last_error", "hint_version", "hint_launch_count",
     "hint_backward_nll", "hint_add_noise", "hint_nll_workspace_bytes", "hint_nll_loss", "hint_adam_step",
+    "hint_householder_matrix", "hint_householder_matrix_backward", "hint_householder_apply",
+    "hint_householder_wgrad_workspace_bytes", "hint_householder_wgrad",
 ]
 
 
@@ -97,6 +99,16 @@ def load():
     lib.hint_adam_step.restype = ctypes.c_int
     lib.hint_adam_step.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                    ctypes.POINTER(i64), f32, f32, f32, f32, f32, f32, i64, vp]
+    lib.hint_householder_matrix.restype = ctypes.c_int
+    lib.hint_householder_matrix.argtypes = [f32p, i32, i32, f32p, vp]
+    lib.hint_householder_matrix_backward.restype = ctypes.c_int
+    lib.hint_householder_matrix_backward.argtypes = [f32p, f32p, f32p, i32, i32, f32p, vp]
+    lib.hint_householder_apply.restype = ctypes.c_int
+    lib.hint_householder_apply.argtypes = [f32p, f32p, i64, i32, i32, f32p, vp]
+    lib.hint_householder_wgrad_workspace_bytes.restype = ctypes.c_size_t
+    lib.hint_householder_wgrad_workspace_bytes.argtypes = [i32]
+    lib.hint_householder_wgrad.restype = ctypes.c_int
+    lib.hint_householder_wgrad.argtypes = [f32p, f32p, i64, i32, f32p, vp, ctypes.c_size_t, vp]
     lib.hint_launch_count.restype = ctypes.c_uint64
     lib.hint_launch_count.argtypes = []
     lib.hint_last_error.restype = ctypes.c_char_p

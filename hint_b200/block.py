@@ -36,6 +36,26 @@ def get_precision() -> str:
     return _mode
 
 
+# The backward is memory-free: autograd keeps only the block OUTPUT and the kernel re-derives every node's input as
+# x_l = (z_l - t) / e(s).  With clamp = 4 the scale e lies in [e^-4, e^4]; the division and the cancellation in z_l - t amplify
+# rounding by up to ~55x per nesting level, so a strongly trained / saturated coupling can lose accuracy in the reconstruction
+# (and with it in the gradients) where the reference, which stores its activations, does not.  `set_backward_check(tol)` makes
+# every forward also keep the block INPUT and every backward compare it with the kernel's reconstruction:
+#   max|x_rec - x| <= tol * max(1, max|x|)   else RuntimeError (or a warning with raise_error=False).
+_bwd_check = None
+
+
+def set_backward_check(tol=1e-3, raise_error=True):
+    """Enable (tol > 0) or disable (tol = None / 0) the reconstruction check of the memory-free backward.  Costs one extra
+    [B, d] tensor per block kept for backward and one write + one read of it."""
+    global _bwd_check
+    _bwd_check = (float(tol), bool(raise_error)) if tol else None
+
+
+def get_backward_check():
+    return _bwd_check
+
+
 def linear_subnet_constructor(c_in, c_out, c_internal):
     """Shape contract of the only subnet the fused kernels implement (hint.py:10-13):
     Linear(c_in, h) - ReLU - Linear(h, h) - ReLU - Linear(h, c_out).  Passing this function (or None) as
@@ -203,20 +223,34 @@ class _CouplingFn(torch.autograd.Function):
         mode = _mode   # the precision mode is fixed per call: backward uses the kernels of the mode the forward ran in
         z, J = plan.forward(x, c, flat, rev, mode=mode)
         ctx.plan, ctx.rev, ctx.mode = plan, rev, mode
-        ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat)
+        ctx.check = _bwd_check if not rev else None
+        ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat, x.detach() if ctx.check else x.new_empty(0))
         return z, J
 
     @staticmethod
     def backward(ctx, dz, dJ):
         if ctx.rev:
             raise NotImplementedError("hint_b200: gradients through the rev=True direction are not implemented yet")
-        z, c, flat = ctx.saved_tensors
+        z, c, flat, x_in = ctx.saved_tensors
         plan = ctx.plan
         if dz is None:
             dz = torch.zeros_like(z)
         if dJ is None:
             dJ = torch.zeros(z.shape[0], dtype=z.dtype, device=z.device)
-        dx, dc, dflat, _ = plan.backward(z, c if plan.dc else None, flat, dz, dJ, mode=ctx.mode, want_dc=ctx.needs_input_grad[1])
+        dx, dc, dflat, xrec = plan.backward(z, c if plan.dc else None, flat, dz, dJ, mode=ctx.mode, want_dc=ctx.needs_input_grad[1],
+                                            want_xrec=ctx.check is not None)
+        if ctx.check is not None:
+            tol, fatal = ctx.check
+            err = float((xrec - x_in).abs().max())
+            scale = max(1.0, float(x_in.abs().max()))
+            if not (err <= tol * scale):
+                msg = (f"hint_b200: the memory-free backward reconstructed the block input with max abs error {err:.3e} "
+                       f"(> {tol:g} * {scale:.3g}) in mode '{ctx.mode}': the coupling is too ill-conditioned for "
+                       "recomputation by inversion; gradients of this step are unreliable (use mode 'fp32' / 'tf32x3' or a smaller clamp)")
+                if fatal:
+                    raise RuntimeError(msg)
+                import warnings
+                warnings.warn(msg)
         return (dx if ctx.needs_input_grad[0] else None, dc if ctx.needs_input_grad[1] else None,
                 dflat if ctx.needs_input_grad[2] else None, None, None)
 

@@ -20,6 +20,7 @@
 #include "plan_tc3.h"
 #include "tc3_launch.h"
 #include "train_ops.h"
+#include "householder.h"
 #include "simt_kernels.cuh"
 #include "tc2_kernels.cuh"
 
@@ -613,6 +614,37 @@ int hint_adam_step(int32_t n_tensors, float* const* params, const float* const* 
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t must be long long");
     CUDA_TRY(train_adam_step(n_tensors, params, grads, exp_avg, exp_avg_sq, reinterpret_cast<const long long*>(sizes), lr, beta1,
                              beta2, eps, weight_decay, grad_clamp, (long long)step, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+int hint_householder_matrix(const float* Vs, int32_t n_reflections, int32_t d, float* W, void* stream) {
+    if (!Vs || !W || d < 1 || d > hh_max_d() || n_reflections < 0) return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
+    CUDA_TRY(hh_matrix(Vs, n_reflections, d, W, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+int hint_householder_matrix_backward(const float* Vs, const float* W, const float* dW, int32_t n_reflections, int32_t d, float* dVs,
+                                     void* stream) {
+    if (!Vs || !W || !dW || !dVs || d < 1 || d > hh_max_d() || n_reflections < 0)
+        return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
+    CUDA_TRY(hh_matrix_backward(Vs, W, dW, n_reflections, d, dVs, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+int hint_householder_apply(const float* x, const float* W, int64_t B, int32_t d, int32_t transpose, float* y, void* stream) {
+    if (B < 0 || d < 1 || d > hh_max_d() || (B > 0 && (!x || !W || !y))) return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
+    if (y == x) return fail(HINT_ERR_INVALID, "y must not alias x");
+    CUDA_TRY(hh_apply(x, W, (long long)B, d, transpose, y, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+size_t hint_householder_wgrad_workspace_bytes(int32_t d) { return d >= 1 && d <= hh_max_d() ? hh_wgrad_workspace_bytes(d) : 0; }
+
+int hint_householder_wgrad(const float* x, const float* dz, int64_t B, int32_t d, float* dW, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    if (B < 0 || d < 1 || d > hh_max_d() || !dW || (B > 0 && (!x || !dz))) return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
+    if (!workspace || workspace_bytes < hh_wgrad_workspace_bytes(d)) return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    CUDA_TRY(hh_wgrad(x, dz, (long long)B, d, dW, workspace, (cudaStream_t)stream));
     return HINT_OK;
 }
 

@@ -1,0 +1,80 @@
+"""Host side of the inter-block Householder mixing (FrEIA ``HouseholderPerm`` as the reference's configs use it,
+e.g. configs/plus_shape/unconditional_hint_4_3.py:60-71).  Thin autograd wrapper over the C ABI (include/hint_b200.h:
+hint_householder_*): W is rebuilt from the reflections by one kernel per call when they are trainable, applied by an FP32 FFMA
+kernel, and differentiated without stored intermediates.  CUDA tensors only - there is no CPU path."""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dense(t):
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
+def householder_matrix(Vs):
+    """W [d, d] = prod_i (I - 2 v_i v_i^T / |v_i|^2), v_i = Vs[i] (no autograd; see HouseholderMix for the differentiable form)."""
+    if not Vs.is_cuda or Vs.dtype != torch.float32:
+        raise RuntimeError("hint_b200.householder_matrix: float32 CUDA tensor required (there is no CPU path)")
+    Vs = _dense(Vs.detach())
+    n, d = Vs.shape
+    with torch.cuda.device(Vs.device):
+        W = torch.empty(d, d, dtype=torch.float32, device=Vs.device)
+        _lib.check(_lib.load().hint_householder_matrix(Vs.data_ptr(), n, d, W.data_ptr(), _stream()))
+    return W
+
+
+def householder_apply(x, W, transpose=False):
+    """y = x W (or x W^T), FP32."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("hint_b200.householder_apply: float32 CUDA tensors required (there is no CPU path)")
+    x, W = _dense(x), _dense(W)
+    B, d = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().hint_householder_apply(x.data_ptr(), W.data_ptr(), B, d, 1 if transpose else 0, y.data_ptr(), _stream()))
+    return y
+
+
+def _wgrad(x, dz):
+    lib = _lib.load()
+    x, dz = _dense(x), _dense(dz)
+    B, d = x.shape
+    with torch.cuda.device(x.device):
+        dW = torch.empty(d, d, dtype=torch.float32, device=x.device)
+        nbytes = lib.hint_householder_wgrad_workspace_bytes(d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.hint_householder_wgrad(x.data_ptr(), dz.data_ptr(), B, d, dW.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    return dW
+
+
+class HouseholderMix(torch.autograd.Function):
+    """y = x W(Vs) (rev=False) or x W(Vs)^T (rev=True).  ``W`` may be passed pre-built (fixed reflections)."""
+
+    @staticmethod
+    def forward(ctx, x, Vs, W, rev):
+        if W is None:
+            W = householder_matrix(Vs)
+        ctx.rev = bool(rev)
+        ctx.save_for_backward(x, Vs, W)
+        return householder_apply(x, W, transpose=rev)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Vs, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = householder_apply(dy, W, transpose=not ctx.rev) if ctx.needs_input_grad[0] else None
+        dVs = None
+        if ctx.needs_input_grad[1]:
+            dW = _wgrad(dy, x) if ctx.rev else _wgrad(x, dy)      # y = x W^T: dW = dy^T x;  y = x W: dW = x^T dy
+            lib = _lib.load()
+            V = _dense(Vs.detach())
+            n, d = V.shape
+            with torch.cuda.device(x.device):
+                dVs = torch.empty_like(V)
+                _lib.check(lib.hint_householder_matrix_backward(V.data_ptr(), W.data_ptr(), dW.data_ptr(), n, d, dVs.data_ptr(), _stream()))
+        return dx, dVs, None, None

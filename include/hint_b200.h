@@ -136,6 +136,23 @@ int hint_adam_step(int32_t n_tensors, float* const* params, const float* const* 
                    float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
                    float weight_decay, float grad_clamp, int64_t step, void* stream);
 
+/* --- inter-block orthogonal mixing: FrEIA `HouseholderPerm` as the reference's configs use it between HINT
+ * blocks (configs/uci_data/miniboone_hint_8.py:60-63 fixed, configs/plus_shape/unconditional_hint_4_3.py:60-71 trainable).
+ * W [d,d] row-major = prod_{i < n_reflections} (I - 2 v_i v_i^T / |v_i|^2), v_i = Vs[i,:]; forward y = x W, reverse y = x W^T,
+ * log|det| = 0.  FrEIA's source is not part of the reference: published definition, parity-unpinned.  1 <= d <= 128.
+ *   hint_householder_matrix           W from Vs (one launch; run once per step when the reflections are trainable)
+ *   hint_householder_matrix_backward  dVs [n_reflections,d] from dW and the W the forward produced (no stored intermediates)
+ *   hint_householder_apply            y = x W (transpose = 0) or x W^T (transpose != 0), FP32 FFMA; also the input gradient
+ *                                     (dx = dy W^T)
+ *   hint_householder_wgrad            dW = x^T dy (deterministic two-stage reduction) */
+int hint_householder_matrix(const float* Vs, int32_t n_reflections, int32_t d, float* W, void* stream);
+int hint_householder_matrix_backward(const float* Vs, const float* W, const float* dW, int32_t n_reflections, int32_t d,
+                                     float* dVs, void* stream);
+int hint_householder_apply(const float* x, const float* W, int64_t B, int32_t d, int32_t transpose, float* y, void* stream);
+size_t hint_householder_wgrad_workspace_bytes(int32_t d);
+int hint_householder_wgrad(const float* x, const float* dz, int64_t B, int32_t d, float* dW, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 const char* hint_last_error(void);
 /* "hint_b200 <version> sm_100a" — lets the host check it loaded the in-tree build */
 const char* hint_version(void);

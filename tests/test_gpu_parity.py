@@ -201,3 +201,35 @@ def test_full_size_properties():
     assert (dx2 - 2 * dx1).abs().max().item() <= 1e-5 * dx1.abs().max().item() + 1e-9
     dx3, _, g3, _ = blk.plan.backward(z, None, blk.flat.detach(), dz, dJ)
     assert torch.equal(g1, g3) and torch.equal(dx1, dx3)   # deterministic reduction (no atomics)
+
+
+def test_backward_reconstruction_check_flags_ill_conditioned_couplings():
+    """the memory-free backward inverts the block (x_l = (z_l - t) / e).  With saturated scales (|s| large, clamp 4:
+    e up to e^4 per level) and |t| >> |e x| the reconstruction loses digits.  set_backward_check keeps the input and compares:
+    a well-conditioned block passes silently, a deliberately saturated one is reported (fp32 and tf32)."""
+    import hint_b200
+    from hint_b200 import HierarchicalAffineCouplingBlock
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    x = torch.randn(512, 20, device=dev)
+    old_mode = hint_b200.get_precision()
+    try:
+        for mode in ("fp32", "tf32"):
+            hint_b200.set_precision(mode)
+            hint_b200.set_backward_check(1e-3 if mode == "fp32" else 2e-2)
+            good = HierarchicalAffineCouplingBlock([(20,)], c_internal=[68, 34, 17, 17]).to(dev)
+            z = good([x.clone().requires_grad_(True)])[0]
+            (0.5 * (z ** 2).sum(1).mean() - good.jac.mean()).backward()          # passes: measured error ~1e-6 (fp32)
+            bad = HierarchicalAffineCouplingBlock([(20,)], c_internal=[68, 34, 17, 17]).to(dev)
+            with torch.no_grad():
+                bad.flat.mul_(40.0)                                               # saturated scales, huge shifts
+            z = bad([x.clone().requires_grad_(True)])[0]
+            loss = 0.5 * (z ** 2).sum(1).mean() - bad.jac.mean()
+            if torch.isfinite(loss):
+                hint_b200.set_backward_check(1e-7, raise_error=True)             # far below what inversion can deliver here
+                z = bad([x.clone().requires_grad_(True)])[0]
+                with pytest.raises(RuntimeError, match="reconstructed the block input"):
+                    (0.5 * (z ** 2).sum(1).mean() - bad.jac.mean()).backward()
+    finally:
+        hint_b200.set_backward_check(None)
+        hint_b200.set_precision(old_mode)
