@@ -290,11 +290,11 @@ def run_ours(args, w, name):
             return total / steps
         return timed_avg
 
-    def build(wl, B, mode, seed_rank=True):
+    def build(wl, B, mode, seed_rank=True, householder=None):
         hint_b200.set_precision(mode)
         torch.manual_seed(0)
         model = HintFlow(wl["d"], wl["n_blocks"], wl["c_internal"], dims_c=[(wl["dc"],)] if wl["dc"] else [],
-                         max_splits=wl["max_splits"]).to(dev)
+                         max_splits=wl["max_splits"], householder=householder).to(dev)
         model.init_like_reference_scripts(0.005)
         broadcast_parameters(model)
         params = [p for p in model.parameters() if p.requires_grad]
@@ -303,9 +303,9 @@ def run_ours(args, w, name):
         x, c = synthetic_batch(torch, B, wl["d"], wl["dc"], dev, 1 + (rank if seed_rank else 0))
         return model, params, opt, trainer, x, c
 
-    def phases(wl, B, mode, steps, warmup):
+    def phases(wl, B, mode, steps, warmup, householder=None):
         """train step / fwd+logdet / inverse of one workload: samples/s (whole job) and the launch count of one train step."""
-        model, params, opt, trainer, x, c = build(wl, B, mode)
+        model, params, opt, trainer, x, c = build(wl, B, mode, householder=householder)
         tavg = make_timed_avg(B * wl["d"] * 4 <= 126e6)
         for _ in range(warmup):
             trainer.step(x, c)
@@ -503,6 +503,18 @@ def run_ours(args, w, name):
             except Exception as e:   # a mode outside a kernel family's envelope is reported, not fatal
                 modes[md] = {"error": str(e)[:200]}
         line["modes"] = modes
+        # the configs' full x-lane: the same blocks with the inter-block HouseholderPerm mixing between them (SURVEY.md 8f-2;
+        # uci configs: fixed reflections, plus_shape hint_4_3: trainable) - FP32 FFMA kernels of this library, not cuBLAS
+        hh = {}
+        for kind in ("fixed", "trainable"):
+            try:
+                ph, keep = phases(w, B, args.mode, 3, 3, householder=kind)
+                del keep
+                hh[kind] = {k: ph[k] for k in ("train_samples_per_s", "train_ms", "launches_per_train_step", "fwd_logdet_samples_per_s",
+                                               "inverse_samples_per_s")}
+            except Exception as e:
+                hh[kind] = {"error": str(e)[:200]}
+        line["with_householder"] = hh
         cfgs = []
         for wn, Bw in CONFIG_SWEEP:
             if wn == name and Bw == B:

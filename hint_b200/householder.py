@@ -3,6 +3,7 @@ e.g. configs/plus_shape/unconditional_hint_4_3.py:60-71).  Thin autograd wrapper
 hint_householder_*): W is rebuilt from the reflections by one kernel per call when they are trainable, applied by an FP32 FFMA
 kernel, and differentiated without stored intermediates.  CUDA tensors only - there is no CPU path."""
 import torch
+import torch.nn as nn
 
 from . import _lib
 
@@ -52,6 +53,21 @@ def _wgrad(x, dz):
     return dW
 
 
+def householder_vs_grad(x, dy, Vs, W, out=None):
+    """Gradient of the reflections for y = x W(Vs): dW = x^T dy (deterministic two-stage reduction), then the chain of
+    reflections walked backwards without stored intermediates.  ``out`` receives the result when given."""
+    dW = _wgrad(x, dy)
+    V = _dense(Vs.detach())
+    n, d = V.shape
+    with torch.cuda.device(x.device):
+        dVs = out if (out is not None and out.is_contiguous() and out.data_ptr() % 16 == 0) else torch.empty_like(V)
+        _lib.check(_lib.load().hint_householder_matrix_backward(V.data_ptr(), _dense(W).data_ptr(), dW.data_ptr(), n, d, dVs.data_ptr(), _stream()))
+        if out is not None and dVs is not out:
+            out.copy_(dVs)
+            dVs = out
+    return dVs
+
+
 class HouseholderMix(torch.autograd.Function):
     """y = x W(Vs) (rev=False) or x W(Vs)^T (rev=True).  ``W`` may be passed pre-built (fixed reflections)."""
 
@@ -78,3 +94,45 @@ class HouseholderMix(torch.autograd.Function):
                 dVs = torch.empty_like(V)
                 _lib.check(lib.hint_householder_matrix_backward(V.data_ptr(), W.data_ptr(), dW.data_ptr(), n, d, dVs.data_ptr(), _stream()))
         return dx, dVs, None, None
+
+
+class HouseholderPerm(nn.Module):
+    """FrEIA ``HouseholderPerm`` (published definition, parity-unpinned): the fixed / learned orthogonal mixing the reference
+    inserts between HINT blocks.  CUDA float32 inputs run on the library kernels above; CPU tensors use the plain PyTorch
+    expressions, which define the semantics (and serve the shim's CPU tests)."""
+
+    def __init__(self, dims_in, dims_c=[], n_reflections=1, fixed=False):
+        super().__init__()
+        assert len(dims_in) == 1 and len(dims_in[0]) == 1, "HouseholderPerm mixes flat feature vectors"
+        self.width = int(dims_in[0][0])
+        self.n_reflections = int(n_reflections)
+        self.fixed = bool(fixed)
+        self.conditional = len(dims_c) > 0          # accepted and ignored: the mixing does not depend on the condition
+        self.Vs = nn.Parameter(torch.randn(self.n_reflections, self.width), requires_grad=not self.fixed)
+        if self.fixed:
+            self.register_buffer("W", self._matrix(self.Vs.detach()), persistent=False)
+
+    @staticmethod
+    def _matrix(Vs):
+        W = torch.eye(Vs.shape[1], dtype=Vs.dtype, device=Vs.device)
+        for v in Vs:
+            W = W - 2.0 * torch.outer(W @ v, v) / torch.dot(v, v)      # W (I - 2 v v^T / |v|^2)
+        return W
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        if self.fixed:
+            self.W = self._matrix(self.Vs.detach())
+
+    def forward(self, x, c=[], rev=False):
+        if x[0].is_cuda and x[0].dtype == torch.float32 and x[0].dim() == 2 and self.width <= 128:
+            return [HouseholderMix.apply(x[0], self.Vs, self.W if self.fixed else None, bool(rev))]
+        W = self.W if self.fixed else self._matrix(self.Vs)
+        return [x[0] @ (W.t() if rev else W)]
+
+    def jacobian(self, x, c=[], rev=False):
+        return 0
+
+    def output_dims(self, input_dims):
+        assert len(input_dims) == 1, "Can only use one input."
+        return input_dims

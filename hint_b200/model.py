@@ -1,21 +1,27 @@
-"""A chain of HINT coupling blocks: the x-lane of the reference configs with the blocks applied back to back
-(e.g. configs/uci_data/miniboone_hint_8.py:55-71 minus the inter-block HouseholderPerm nodes, which are FrEIA code
-and not part of hint.py).  Used by bench.py, the DP trainer and the smoke test; the reference's own scripts build
-the same chain through the FrEIA graph shim instead."""
+"""A chain of HINT coupling blocks: the x-lane of the reference configs (e.g. configs/uci_data/miniboone_hint_8.py:55-71),
+with the blocks applied back to back or - ``householder='fixed' | 'trainable'`` - with the inter-block HouseholderPerm mixing
+of the configs between them (FrEIA code, published definition, parity-unpinned).  Used by bench.py, the DP trainer and the smoke
+test; the reference's own scripts build the same chain through the FrEIA graph shim instead."""
 import torch
 import torch.nn as nn
 
 from .block import HierarchicalAffineCouplingBlock
+from .householder import HouseholderPerm
 
 
 class HintFlow(nn.Module):
-    def __init__(self, d, n_blocks, c_internal, dims_c=(), clamp=4.0, max_splits=-1, min_split_size=2):
+    def __init__(self, d, n_blocks, c_internal, dims_c=(), clamp=4.0, max_splits=-1, min_split_size=2, householder=None):
         super().__init__()
         self.d = int(d)
         self.blocks = nn.ModuleList([
             HierarchicalAffineCouplingBlock([(d,)], dims_c=list(dims_c), c_internal=list(c_internal), clamp=clamp,
                                             max_splits=max_splits, min_split_size=min_split_size)
             for _ in range(n_blocks)])
+        if householder not in (None, "fixed", "trainable"):
+            raise ValueError("householder must be None, 'fixed' or 'trainable'")
+        # perms[i] mixes the output of block i before block i + 1 ({'fixed': ..., 'n_reflections': d} in the configs)
+        self.perms = nn.ModuleList([HouseholderPerm([(d,)], n_reflections=d, fixed=householder == "fixed")
+                                    for _ in range(n_blocks - 1)]) if householder else None
 
     @property
     def flops_per_sample(self):
@@ -25,16 +31,23 @@ class HintFlow(nn.Module):
         """-> (z, logdet).  rev=True applies the inverse blocks in reverse order."""
         cs = [] if c is None else [c]
         J = None
-        for blk in (reversed(self.blocks) if rev else self.blocks):
+        n = len(self.blocks)
+        for i in (range(n - 1, -1, -1) if rev else range(n)):
+            if self.perms is not None and not rev and i > 0:
+                x = self.perms[i - 1]([x])[0]
+            blk = self.blocks[i]
             x = blk([x], c=cs, rev=rev)[0]
             J = blk.jac if J is None else J + blk.jac
+            if self.perms is not None and rev and i > 0:
+                x = self.perms[i - 1]([x], rev=True)[0]
         return x, J
 
     def init_like_reference_scripts(self, init_scale=0.005, generator=None):
         """p = init_scale * randn for every trainable parameter (train_unconditional.py:165-167)."""
         with torch.no_grad():
             for p in self.parameters():
-                p.copy_(init_scale * torch.randn(p.shape, generator=generator, device=p.device, dtype=p.dtype))
+                if p.requires_grad:
+                    p.copy_(init_scale * torch.randn(p.shape, generator=generator, device=p.device, dtype=p.dtype))
         return self
 
 

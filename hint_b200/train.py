@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .block import get_precision
+from .householder import householder_apply, householder_matrix, householder_vs_grad
 
 
 def _stream():
@@ -114,6 +115,11 @@ class FusedTrainStep:
         for blk in model.blocks:
             if blk.flat.grad is None:
                 blk.flat.grad = torch.zeros_like(blk.flat)
+        self.perms = getattr(model, "perms", None)
+        if self.perms is not None:
+            for pm in self.perms:
+                if not pm.fixed and pm.Vs.grad is None:
+                    pm.Vs.grad = torch.zeros_like(pm.Vs)
 
     @torch.no_grad()
     def step(self, x, c=None):
@@ -122,8 +128,14 @@ class FusedTrainStep:
         B = x.shape[0]
         h = add_noise(x, self.noise, self.seed, self.calls) if self.noise else x
         self.calls += 1
+        perms = self.perms
+        Ws = None
+        if perms is not None:      # the mixing matrices of this step: constants, or rebuilt from the trainable reflections (one launch each)
+            Ws = [pm.W if pm.fixed else householder_matrix(pm.Vs) for pm in perms]
         zs, Js = [], []
-        for blk in model.blocks:
+        for i, blk in enumerate(model.blocks):
+            if Ws is not None and i > 0:
+                h = householder_apply(h, Ws[i - 1])
             h, Jb = blk.plan.forward(h, c, blk.flat.detach(), False, mode=mode)
             zs.append(h)
             Js.append(Jb)
@@ -138,6 +150,13 @@ class FusedTrainStep:
             zs[i] = None
             if self.world > 1:
                 handles.append(dist.all_reduce(blk.flat.grad, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            if Ws is not None and i > 0:      # through the mixing in front of block i: y = z_{i-1} W
+                pm = perms[i - 1]
+                if not pm.fixed:
+                    householder_vs_grad(zs[i - 1], dz, pm.Vs, Ws[i - 1], out=pm.Vs.grad)
+                    if self.world > 1:
+                        handles.append(dist.all_reduce(pm.Vs.grad, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+                dz = householder_apply(dz, Ws[i - 1], transpose=True)
         for hd in handles:
             hd.wait()
         self.opt.step()

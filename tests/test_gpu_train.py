@@ -113,7 +113,10 @@ def test_backward_nll_equals_backward_with_materialised_gradient(dev, name, d, d
 
 
 @pytest.mark.parametrize("wl", [dict(d=43, ci=[67, 33, 16, 8], nb=3, mode="tf32"), dict(d=8, ci=[128, 64, 32, 16], nb=2, mode="tf32"),
-                                dict(d=20, ci=[68, 34, 17, 17], nb=2, mode="fp32")], ids=["d43_tf32", "gas_tf32", "lens_fp32"])
+                                dict(d=20, ci=[68, 34, 17, 17], nb=2, mode="fp32"),
+                                dict(d=20, ci=[68, 34, 17, 17], nb=3, mode="fp32", hh="fixed"),
+                                dict(d=43, ci=[67, 33, 16, 8], nb=3, mode="fp32", hh="trainable")],
+                         ids=["d43_tf32", "gas_tf32", "lens_fp32", "lens_fp32_householder_fixed", "d43_fp32_householder_trainable"])
 def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
     """Steps without noise against module forward + nll_loss + backward + clamp_ + torch.optim.Adam.  After ONE step the
     parameters agree to 2e-6 * max|p| in every mode (same kernels, same inputs; only Adam's fp32 association differs).  After
@@ -125,14 +128,19 @@ def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
     hint_b200.set_precision(wl["mode"])
     try:
         torch.manual_seed(0)
-        ma = HintFlow(wl["d"], wl["nb"], wl["ci"]).to(dev).init_like_reference_scripts(0.05)
-        mb = HintFlow(wl["d"], wl["nb"], wl["ci"]).to(dev)
+        ma = HintFlow(wl["d"], wl["nb"], wl["ci"], householder=wl.get("hh")).to(dev).init_like_reference_scripts(0.05)
+        mb = HintFlow(wl["d"], wl["nb"], wl["ci"], householder=wl.get("hh")).to(dev)
         mb.load_state_dict(ma.state_dict())
+        if wl.get("hh") == "trainable":      # reflections of unit scale (0.05 * randn would still be a valid reflection: only the direction counts)
+            with torch.no_grad():
+                for pa, pb in zip(ma.perms, mb.perms):
+                    pa.Vs.normal_()
+                    pb.Vs.copy_(pa.Vs)
         B = 1000
         x = torch.randn(B, wl["d"], device=dev)
-        opt_a = FusedClampAdam(list(ma.parameters()), grad_clamp=5.0, **ADAM)
+        opt_a = FusedClampAdam([p for p in ma.parameters() if p.requires_grad], grad_clamp=5.0, **ADAM)
         tr = FusedTrainStep(ma, opt_a, noise=0.0)
-        opt_b = torch.optim.Adam(mb.parameters(), **ADAM)
+        opt_b = torch.optim.Adam([p for p in mb.parameters() if p.requires_grad], **ADAM)
         n0 = hint_b200._lib.load().hint_launch_count()
         for it in range(3):
             la = tr.step(x)
@@ -141,10 +149,16 @@ def test_fused_train_step_matches_the_reference_surface_step(dev, wl):
             lb = nll_loss(z, J)
             lb.backward()
             for p in mb.parameters():
-                p.grad.clamp_(-5.0, 5.0)
+                if p.grad is not None:
+                    p.grad.clamp_(-5.0, 5.0)
             opt_b.step()
             assert abs(float(la[0]) - float(lb.detach())) <= 1e-4 * max(1.0, abs(float(lb.detach())))
             tol = 2e-6 if it == 0 else (1e-5 if wl["mode"] == "fp32" else 2e-2)
+            if wl.get("hh"):
+                # with the mixing between the blocks the two paths differ in the last bits of dz (kernel vs autograd order of the
+                # same FP32 products) and Adam's normalised update carries that into the parameters; trainable reflections add the
+                # gradient through a product of 43 reflections (kernel vs autograd: 1e-4 relative)
+                tol *= 10 if wl["hh"] == "fixed" else 100
             with torch.no_grad():
                 for pa, pb in zip(ma.parameters(), mb.parameters()):
                     assert float((pa - pb).abs().max()) <= tol * float(pb.abs().max()), (it, float((pa - pb).abs().max()))
