@@ -215,6 +215,36 @@ class TreePlan:
         return dx, dc, dflat, xrec
 
 
+def _inverse_graph(plan, x, c, flat):
+    """The inverse transport of one block written with differentiable PyTorch ops (hint.py:82-96, root coupling first, then the
+    children), on the tensors' own (CUDA) device.  Used ONLY to differentiate the rev=True direction, which the reference never
+    does in its scripts (model_inverse always runs under no_grad / detach) but its autograd would allow: the fused kernels cover
+    the forward-direction backward, this keeps the rev direction differentiable instead of raising.  Not a compute path of
+    forward / inverse / training."""
+    alpha = plan.clamp * 0.636
+    views = {name: flat[off:off + math.prod(shape)].view(shape) for name, off, shape in plan.entries}
+    cols = list(x.unbind(dim=1))
+    J = x.new_zeros(x.shape[0])
+    order = sorted(range(len(plan.nodes)), key=lambda i: plan.nodes[i]["depth"])     # root level first (hint.py:85-88)
+    for i in order:
+        nd, path = plan.nodes[i], plan.paths[i]
+        lo, k, hi = nd["lo"], nd["k"], nd["hi"]
+        a = torch.stack(cols[lo:lo + k], dim=1)
+        if plan.dc:
+            a = torch.cat([a, c], dim=1)
+
+        def mlp(net):
+            h = torch.relu(torch.addmm(views[f"{path}.{net}.0.bias"], a, views[f"{path}.{net}.0.weight"].t()))
+            h = torch.relu(torch.addmm(views[f"{path}.{net}.2.bias"], h, views[f"{path}.{net}.2.weight"].t()))
+            return torch.addmm(views[f"{path}.{net}.4.bias"], h, views[f"{path}.{net}.4.weight"].t())
+        la = alpha * torch.atan(mlp("s"))
+        xl = (torch.stack(cols[lo + k:hi], dim=1) - mlp("t")) * torch.exp(-la)
+        J = J - la.sum(dim=1)
+        for j in range(hi - lo - k):
+            cols[lo + k + j] = xl[:, j]
+    return torch.stack(cols, dim=1), J
+
+
 class _CouplingFn(torch.autograd.Function):
     """z, logdet = block(x, c).  Saves only the OUTPUT z (+ c, params); backward re-derives the rest."""
 
@@ -224,15 +254,31 @@ class _CouplingFn(torch.autograd.Function):
         z, J = plan.forward(x, c, flat, rev, mode=mode)
         ctx.plan, ctx.rev, ctx.mode = plan, rev, mode
         ctx.check = _bwd_check if not rev else None
-        ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat, x.detach() if ctx.check else x.new_empty(0))
+        ctx.save_for_backward(z, c if c is not None else x.new_empty(0), flat, x.detach() if (ctx.check or rev) else x.new_empty(0))
         return z, J
 
     @staticmethod
     def backward(ctx, dz, dJ):
-        if ctx.rev:
-            raise NotImplementedError("hint_b200: gradients through the rev=True direction are not implemented yet")
         z, c, flat, x_in = ctx.saved_tensors
         plan = ctx.plan
+        if ctx.rev:
+            # gradients through the inverse: differentiate the PyTorch restatement at the saved INPUT of the rev call
+            with torch.enable_grad():
+                xi = x_in.detach().requires_grad_(True)
+                ci = c.detach().requires_grad_(True) if plan.dc else None
+                fi = flat.detach().requires_grad_(True)
+                y, Jr = _inverse_graph(plan, xi, ci, fi)
+                outs, grads = [], []
+                if dz is not None:
+                    outs.append(y); grads.append(dz)
+                if dJ is not None:
+                    outs.append(Jr); grads.append(dJ)
+                ins = [xi, fi] + ([ci] if plan.dc else [])
+                g = torch.autograd.grad(outs, ins, grads, allow_unused=True)
+            gx, gf = g[0], g[1]
+            gc = g[2] if plan.dc else None
+            return (gx if ctx.needs_input_grad[0] else None, gc if ctx.needs_input_grad[1] else None,
+                    gf if ctx.needs_input_grad[2] else None, None, None)
         if dz is None:
             dz = torch.zeros_like(z)
         if dJ is None:
@@ -327,10 +373,45 @@ class HierarchicalAffineCouplingBlock(nn.Module):
         d = int(dims_in[0][0])
         dc = int(sum(dims_c[i][0] for i in range(len(dims_c))))
         self.dims_c = [tuple(t) for t in dims_c]
-        self.plan = TreePlan(d, dc, list(c_internal), clamp, max_splits, min_split_size, reshuffle)
+        # reshuffle=True (hint.py:36-39,64-65,93-94): every tree node mixes its inputs with a FIXED orthogonal matrix before the
+        # split.  The mixings are applied top-down while the recursion descends and the couplings bottom-up while it returns, so
+        # all of them compose into ONE d x d orthogonal matrix M = D_0 D_1 ... (D_l = block-diagonal of the depth-l nodes' W) in
+        # front of the un-shuffled tree: forward x M -> tree, inverse tree^-1 -> . M^T, log|det| unchanged.  The tree runs in the
+        # fused kernels as always, the mixing in hint_householder_apply (FP32).  W follows the published FrEIA definition
+        # (product of d_node random Householder reflections, parity-unpinned: FrEIA's source is not part of the reference).
+        self.plan = TreePlan(d, dc, list(c_internal), clamp, max_splits, min_split_size, False)
         self.flat = nn.Parameter(torch.empty(self.plan.n_params, dtype=torch.float32))
+        self.reshuffle = bool(reshuffle)
+        if self.reshuffle:
+            if d > 128:
+                raise NotImplementedError("hint_b200: reshuffle=True is implemented for d <= 128")
+            for i, nd in enumerate(self.plan.nodes):      # fixed reflections: buffers (not trainable), saved under the reference's names
+                self.register_buffer(f"_perm_vs_{i}", torch.randn(nd["hi"] - nd["lo"], nd["hi"] - nd["lo"]), persistent=False)
+            self.register_buffer("perm_M", self._compose_perm(), persistent=False)
+            self.register_buffer("_no_vs", torch.zeros(1), persistent=False)
         self.reset_parameters()
         self.jac = None
+
+    @property
+    def perm_vs(self):
+        return [getattr(self, f"_perm_vs_{i}") for i in range(len(self.plan.nodes))]
+
+    def _compose_perm(self):
+        d = self.plan.d
+        depth = max(nd["depth"] for nd in self.plan.nodes)
+        M = torch.eye(d, dtype=torch.float64)
+        for lv in range(depth + 1):
+            D = torch.eye(d, dtype=torch.float64)
+            for nd, vs in zip(self.plan.nodes, self.perm_vs):
+                if nd["depth"] != lv:
+                    continue
+                n = nd["hi"] - nd["lo"]
+                W = torch.eye(n, dtype=torch.float64)
+                for v in vs.detach().double().cpu():
+                    W = W - 2.0 * torch.outer(W @ v, v) / torch.dot(v, v)
+                D[nd["lo"]:nd["hi"], nd["lo"]:nd["hi"]] = W
+            M = M @ D
+        return M.float().to(self.flat.device)
 
     # -- parameters ------------------------------------------------------------------------------
     def reset_parameters(self):
@@ -361,6 +442,9 @@ class HierarchicalAffineCouplingBlock(nn.Module):
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         for name, v in self.named_views().items():
             destination[prefix + name] = v if keep_vars else v.detach().clone()
+        if self.reshuffle:      # the reference keeps one HouseholderPerm per tree node: <path>.perm.Vs
+            for i, vs in enumerate(self.perm_vs):
+                destination[prefix + self.plan.paths[i] + ".perm.Vs"] = vs if keep_vars else vs.detach().clone()
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         views = self.named_views()
@@ -378,6 +462,16 @@ class HierarchicalAffineCouplingBlock(nn.Module):
                 continue
             with torch.no_grad():
                 v.copy_(src)
+        if self.reshuffle:
+            for i, vs in enumerate(self.perm_vs):
+                key = prefix + self.plan.paths[i] + ".perm.Vs"
+                if key not in state_dict:
+                    missing_keys.append(key)
+                    continue
+                seen.add(key)
+                with torch.no_grad():
+                    vs.copy_(state_dict[key])
+            self.perm_M = self._compose_perm()
         if strict:
             for key in state_dict.keys():
                 if key.startswith(prefix) and key not in seen:
@@ -389,10 +483,16 @@ class HierarchicalAffineCouplingBlock(nn.Module):
         cc = None
         if self.plan.dc:
             cc = c[0] if len(c) == 1 else torch.cat(list(c), dim=1)
+        if self.reshuffle and not rev:
+            from .householder import HouseholderMix
+            x0 = HouseholderMix.apply(x0, self._no_vs, self.perm_M, False)
         if torch.is_grad_enabled() and (x0.requires_grad or self.flat.requires_grad or (cc is not None and cc.requires_grad)):
             z, self.jac = _CouplingFn.apply(x0, cc, self.flat, self.plan, bool(rev))
         else:
             z, self.jac = self.plan.forward(x0, cc, self.flat.detach(), bool(rev))
+        if self.reshuffle and rev:
+            from .householder import HouseholderMix
+            z = HouseholderMix.apply(z, self._no_vs, self.perm_M, True)
         return [z]
 
     def jacobian(self, x, c=[], rev=False):

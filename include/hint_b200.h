@@ -72,7 +72,9 @@ typedef struct hint_node_info {
 /* --- plan: replaces HierarchicalAffineCouplingTree.__init__ (hint.py:25-54) and the ctor argument
  * checks of HierarchicalAffineCouplingBlock.__init__ (hint.py:108-122).
  * c_internal/n_internal: hidden widths per depth (empty -> [d], last entry repeats).
- * reshuffle != 0 is rejected with HINT_ERR_UNSUPPORTED (FrEIA HouseholderPerm, parity unpinned). */
+ * reshuffle != 0 is rejected with HINT_ERR_UNSUPPORTED at this level: the per-node mixings of hint.py:36-39,64-65,93-94 compose
+ * into ONE d x d orthogonal matrix in front of the un-shuffled tree, which the host applies with hint_householder_apply (see
+ * hint_b200/block.py); the plan itself is always the un-shuffled tree. */
 int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n_internal, double clamp,
                      int32_t max_splits, int32_t min_split_size, int32_t reshuffle, hint_plan_t** out);
 void hint_plan_destroy(hint_plan_t* plan);

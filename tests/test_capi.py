@@ -73,7 +73,8 @@ def test_ctor_errors_mirror_reference_surface():
     with pytest.raises(NotImplementedError):
         HierarchicalAffineCouplingBlock([(8,)], subnet_constructor=lambda a, b, c: None)
     with pytest.raises(NotImplementedError):
-        HierarchicalAffineCouplingBlock([(8,)], reshuffle=True)
+        HierarchicalAffineCouplingBlock([(200,)], c_internal=[8], reshuffle=True)   # the composed mixing kernel covers d <= 128
+    assert HierarchicalAffineCouplingBlock([(8,)], reshuffle=True).perm_M.shape == (8, 8)
     with pytest.raises(ValueError):
         HierarchicalAffineCouplingBlock([(1,)])
     blk = HierarchicalAffineCouplingBlock([(8,)], subnet_constructor=hint_b200.linear_subnet_constructor)
@@ -98,3 +99,47 @@ def test_import_shim_names():
     import hint
     assert hint.HierarchicalAffineCouplingBlock is HierarchicalAffineCouplingBlock
     assert callable(hint.linear_subnet_constructor)
+
+
+@pytest.mark.parametrize("name", ["reshuffle_d13", "reshuffle_cond_d10_ms1"])
+def test_reshuffle_composes_into_one_matrix_in_front_of_the_tree(name):
+    """hint.py:36-39,64-65,93-94 with reshuffle=True, golden vectors from the REAL module (oracle/gen_golden_reshuffle.py, the
+    published HouseholderPerm definition injected): the block's composed matrix perm_M followed by the UN-shuffled tree (oracle)
+    reproduces the reference's forward, log-det and inverse to 1e-12 (fp64), and the reference's state_dict names round-trip."""
+    from conftest import load_golden
+    g = load_golden(name)
+    meta = g["meta"]
+    kw = dict(meta["kwargs"])
+    blk = HierarchicalAffineCouplingBlock([(meta["d"],)], dims_c=[tuple(t) for t in meta["dims_c"]], **kw)
+    sd = blk.state_dict()
+    perm_keys = sorted(k for k in sd if k.endswith("perm.Vs"))
+    assert perm_keys == sorted(k[3:] for k in g if k.startswith("vs:"))
+    for k in perm_keys:
+        sd[k] = torch.from_numpy(g["vs:" + k]).float()
+    blk.load_state_dict(sd)
+    assert blk.plan.n_params == g["params"].size       # the fixed reflections are not trainable parameters
+    # compose in fp64 from the loaded reflections (perm_M itself is the fp32 copy the kernels use)
+    M = torch.eye(meta["d"], dtype=torch.float64)
+    depth = max(nd["depth"] for nd in blk.plan.nodes)
+    for lv in range(depth + 1):
+        D = torch.eye(meta["d"], dtype=torch.float64)
+        for nd, path in zip(blk.plan.nodes, [blk.plan.paths[i] for i in range(len(blk.plan.nodes))]):
+            if nd["depth"] != lv:
+                continue
+            n = nd["hi"] - nd["lo"]
+            W = torch.eye(n, dtype=torch.float64)
+            for v in torch.from_numpy(g["vs:" + path + ".perm.Vs"]):
+                W = W - 2.0 * torch.outer(W @ v, v) / torch.dot(v, v)
+            D[nd["lo"]:nd["hi"], nd["lo"]:nd["hi"]] = W
+        M = M @ D
+    assert float((blk.perm_M.double() - M).abs().max()) < 1e-6
+    pk = plan_kwargs(meta)
+    plan = O.build_plan(pk["d"], pk["dc"], pk["c_internal"], pk["max_splits"], pk["min_split_size"])
+    f64 = torch.from_numpy(g["params"])
+    x = torch.from_numpy(g["x"])
+    c = torch.from_numpy(g["c"]) if "c" in g else None
+    z, J = O.forward(plan, f64, x @ M, c, clamp=pk["clamp"])
+    assert float((z - torch.from_numpy(g["z64"])).abs().max()) < 1e-12 and float((J - torch.from_numpy(g["J64"])).abs().max()) < 1e-12
+    xi, Ji = O.forward(plan, f64, x, c, rev=True, clamp=pk["clamp"])
+    assert float((xi @ M.t() - torch.from_numpy(g["xinv64"])).abs().max()) < 1e-12
+    assert float((Ji - torch.from_numpy(g["Jinv64"])).abs().max()) < 1e-12

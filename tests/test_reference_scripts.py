@@ -168,12 +168,6 @@ def test_every_config_of_the_reference_builds_through_the_shim(reference_env):
             name = d.replace("/", ".") + "." + f[:-3]
             try:
                 m = importlib.import_module(name)
-            except NotImplementedError as e:
-                # the one ablation with reshuffle=True (unconditional_hint_4_3_reshuffle): rejected loudly, FrEIA's in-tree
-                # HouseholderPerm semantics are unpinned
-                assert "reshuffle" in name and "reshuffle" in str(e), (name, e)
-                stale.append((name, "reshuffle=True is rejected"))
-                continue
             except (ImportError, TypeError, AttributeError) as e:
                 # the reference's own stale files (they import the abstract FourierCurveModel) - not the shim's
                 if "FrEIA" in str(e) or "hint" in str(e).lower():
@@ -187,4 +181,5 @@ def test_every_config_of_the_reference_builds_through_the_shim(reference_env):
                 n_all = sum(p.numel() for p in m.model.params_trainable)
                 assert expected[name] in (n_hint, n_all), (name, n_hint, n_all)
             built += 1
+    assert "configs.plus_shape.unconditional_hint_4_3_reshuffle" in sys.modules      # reshuffle=True builds too
     assert built >= 60, (built, stale)
