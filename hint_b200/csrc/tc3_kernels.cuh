@@ -277,26 +277,30 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         const uint32_t a0 = lane_base + (uint32_t)e.a;
                         unsigned char* im = img_ptr(e.c);
                         const bool to_img = (e.flags & T3H_IMG) != 0;
-                        for (int q = q0; q < q1; q += 32) {
-                            float v[2][16];
-                            const int nb = (q1 - q) >> 4;
+                        // 16 columns: relu + tf32 rounding in place (A operand of the next GEMM) (+ image: operand of dW / relu mask)
+                        auto finish16 = [&](int q, float (&v)[16]) {
 #pragma unroll
-                            for (int u = 0; u < 2; ++u)
-                                if (u < nb) ld16(a0 + q + 16 * u, v[u]);
-                            wait_ld();
+                            for (int j = 0; j < 16; ++j) v[j] = t3_round(fmaxf(v[j], 0.f));
+                            st16(a0 + q, v);
+                            if (to_img) {
+                                unsigned char* ib = im + (uint32_t)(q >> 3) * 1024u;
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                if (u < nb) {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) v[u][j] = t3_round(fmaxf(v[u][j], 0.f));
-                                    st16(a0 + q + 16 * u, v[u]);
-                                    if (to_img) {
-                                        unsigned char* ib = im + (uint32_t)((q + 16 * u) >> 3) * 1024u;
-#pragma unroll
-                                        for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]) = v[u][j];
-                                    }
-                                }
+                                for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]) = v[j];
                             }
+                        };
+                        int q = q0;
+                        for (; q + 32 <= q1; q += 32) {       // two loads in flight
+                            float v0[16], v1[16];
+                            ld16(a0 + q, v0); ld16(a0 + q + 16, v1);
+                            wait_ld();
+                            finish16(q, v0);
+                            finish16(q + 16, v1);
+                        }
+                        if (q < q1) {
+                            float v0[16];
+                            ld16(a0 + q, v0);
+                            wait_ld();
+                            finish16(q, v0);
                         }
                         if (wg == kWG - 1 && (e.flags & T3H_ONES)) {
                             float o[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -398,35 +402,54 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         const int q0 = min(wg * slice, ncols), q1 = min(q0 + slice, ncols);
                         const uint32_t a0 = lane_base + (uint32_t)e.a;
                         unsigned char* imo = img_ptr(e.c);
-                        const bool mask_tmem = (e.flags & T3D_MASK_TMEM) != 0;
-                        const uint32_t m0 = lane_base + (uint32_t)e.e;
-                        const unsigned char* imm = mask_tmem ? imo : img_ptr(e.e);
-                        for (int q = q0; q < q1; q += 32) {
-                            float v[2][16], hm[2][16];
-                            const int nb = (q1 - q) >> 4;
+                        // 16 columns: v = relu'(mask) ? round(v) : 0 -> TMEM (A operand of the next dgrad GEMM) + image (operand of dW)
+                        auto finish16 = [&](int q, float (&v)[16], const float (&hm)[16]) {
+                            unsigned char* ib = imo + (uint32_t)(q >> 3) * 1024u;
 #pragma unroll
-                            for (int u = 0; u < 2; ++u)
-                                if (u < nb) {
-                                    ld16(a0 + q + 16 * u, v[u]);
-                                    if (mask_tmem) ld16(m0 + q + 16 * u, hm[u]);
-                                    else {
-                                        const unsigned char* ib = imm + (uint32_t)((q + 16 * u) >> 3) * 1024u;
+                            for (int j = 0; j < 16; ++j) {
+                                v[j] = hm[j] > 0.f ? t3_round(v[j]) : 0.f;
+                                *reinterpret_cast<float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]) = v[j];
+                            }
+                            st16(a0 + q, v);
+                        };
+                        if (e.flags & T3D_MASK_TMEM) {      // relu mask = the forward activation still in TMEM
+                            const uint32_t m0 = lane_base + (uint32_t)e.e;
+                            int q = q0;
+                            for (; q + 32 <= q1; q += 32) {   // two loads in flight
+                                float v0[16], v1[16], h0[16], h1[16];
+                                ld16(a0 + q, v0); ld16(m0 + q, h0); ld16(a0 + q + 16, v1); ld16(m0 + q + 16, h1);
+                                wait_ld();
+                                finish16(q, v0, h0);
+                                finish16(q + 16, v1, h1);
+                            }
+                            if (q < q1) {
+                                float v0[16], h0[16];
+                                ld16(a0 + q, v0); ld16(m0 + q, h0);
+                                wait_ld();
+                                finish16(q, v0, h0);
+                            }
+                        } else {                            // relu mask = the forward activation image in shared memory
+                            const unsigned char* imm = img_ptr(e.e);
+                            auto mask16 = [&](int q, float (&hm)[16]) {
+                                const unsigned char* ib = imm + (uint32_t)(q >> 3) * 1024u;
 #pragma unroll
-                                        for (int j = 0; j < 16; ++j) hm[u][j] = *reinterpret_cast<const float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]);
-                                    }
-                                }
-                            wait_ld();
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                if (u < nb) {
-                                    unsigned char* ib = imo + (uint32_t)((q + 16 * u) >> 3) * 1024u;
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        v[u][j] = hm[u][j] > 0.f ? t3_round(v[u][j]) : 0.f;
-                                        *reinterpret_cast<float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]) = v[u][j];
-                                    }
-                                    st16(a0 + q + 16 * u, v[u]);
-                                }
+                                for (int j = 0; j < 16; ++j) hm[j] = *reinterpret_cast<const float*>(ib + (uint32_t)(j >> 3) * 1024u + xo[j & 7]);
+                            };
+                            int q = q0;
+                            for (; q + 32 <= q1; q += 32) {
+                                float v0[16], v1[16], h0[16], h1[16];
+                                ld16(a0 + q, v0); ld16(a0 + q + 16, v1);
+                                mask16(q, h0); mask16(q + 16, h1);
+                                wait_ld();
+                                finish16(q, v0, h0);
+                                finish16(q + 16, v1, h1);
+                            }
+                            if (q < q1) {
+                                float v0[16], h0[16];
+                                ld16(a0 + q, v0);
+                                mask16(q, h0);
+                                wait_ld();
+                                finish16(q, v0, h0);
                             }
                         }
                         break;
@@ -444,7 +467,9 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         break;
                     }
                     case T3E_FLUSH: {
-                        // accumulator rows = features on the lanes; this lane's node decides which columns are real
+                        // accumulator rows = features on the lanes; this lane's node decides which column CHUNKS are real.  A chunk
+                        // of 16 columns is flushed whole when it intersects the lane's ranges (node widths are padded to 16, so the
+                        // hidden ranges are chunk-aligned; the few extra columns land in partial-buffer slots no parameter maps to).
                         int c0 = 0, c1 = 0;
                         bool found = false;
                         if (row < e.e) {
@@ -465,19 +490,19 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         // accumulate into the CTA's private, L2-resident partial buffer.  Every address is owned by one thread and
                         // tiles are sequential, so a reduction without return value (RED: no L2 round trip on the critical path)
                         // is still a deterministic, uncontended accumulation; the first tile stores.
-                        auto in_range = [&](int col) { return (col >= c0 && col < c1) || (x0 >= 0 && col >= x0 && col < x1); };
                         for (int q = 16 * wg; q < ncols; q += 16 * kWG) {
                             float v[16];
                             ld16(lane_base + (uint32_t)(e.a + q), v);
                             wait_ld();
-                            if (found) {
+                            const bool live = found && ((q < c1 && q + 16 > c0) || (x0 >= 0 && q < x1 && q + 16 > x0));
+                            if (live) {
+                                float* p0 = pp + (size_t)q * 128;
+                                if (first_tile) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int col = q + j;
-                                    if (in_range(col)) {
-                                        float* p1 = pp + (size_t)col * 128;
-                                        if (first_tile) __stcg(p1, v[j]); else atomicAdd(p1, v[j]);
-                                    }
+                                    for (int j = 0; j < 16; ++j) __stcg(p0 + (size_t)j * 128, v[j]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) atomicAdd(p0 + (size_t)j * 128, v[j]);
                                 }
                             }
                         }
