@@ -79,7 +79,7 @@ struct DevPlan {
     DevTc tc;
     DevMma mma;
     DevChain chain;
-    DevTc3 tc3;
+    DevTc3 tc3, tc3f, tc3i;   // training kernel; the same machine running the forward / inverse transport
     int* pack_src = nullptr;
     int* unpack_src = nullptr;
     int num_sms = 0;
@@ -91,7 +91,7 @@ struct hint_plan {
     Plan p;
     MmaPlan mma;
     ChainPlan chain;
-    T3Plan tc3;
+    T3Plan tc3, tc3f, tc3i;
     TcSchedule tc;
     T2Host tc2;
     std::mutex mu;
@@ -164,6 +164,10 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     }
     if (hp->tc3.ok) {
         CUDA_TRY(tc3_setup(hp->tc3, d.num_sms, d.tc3));
+    }
+    if (hp->tc3f.ok && hp->tc3i.ok) {
+        CUDA_TRY(tc3_setup(hp->tc3f, d.num_sms, d.tc3f));
+        CUDA_TRY(tc3_setup(hp->tc3i, d.num_sms, d.tc3i));
     }
     if (hp->tc.ok) {
         CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
@@ -285,6 +289,8 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
     build_chain_plan(hp->p, hp->chain);
     if (hp->chain.ok && !chain_fits(hp->p, hp->chain, &hp->chain.why)) hp->chain.ok = false;
     build_tc3_plan(hp->p, hp->tc3);
+    build_tc3_plan(hp->p, hp->tc3f, T3K_FORWARD);
+    build_tc3_plan(hp->p, hp->tc3i, T3K_INVERSE);
     build_tc_schedule(hp->p, hp->tc);
     build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
@@ -305,6 +311,8 @@ void hint_plan_destroy(hint_plan_t* hp) {
         mma_free(d.mma);
         chain_free(d.chain);
         tc3_free(d.tc3);
+        tc3_free(d.tc3f);
+        tc3_free(d.tc3i);
         cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
@@ -354,6 +362,7 @@ size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     if (hp->mma.ok) bytes = std::max(bytes, mma_packed_bytes(hp->mma));
     if (hp->chain.ok) bytes = std::max(bytes, align256((size_t)hp->chain.n_packed * 4));
     if (hp->tc3.ok) bytes = std::max(bytes, align256((size_t)hp->tc3.n_packed * 4));
+    if (hp->tc3f.ok) bytes = std::max(bytes, align256((size_t)std::max(hp->tc3f.n_packed, hp->tc3i.n_packed) * 4));
     if (which == HINT_WS_BACKWARD) {
         DevPlan* d = nullptr;
         if (get_dev(hp, &d) != HINT_OK) return 0;
@@ -407,7 +416,19 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     // block fits its TMEM envelope (measured 1.9 ms vs 4.0 ms per 2^20 samples on the d=43 hint_8 block), the warp-MMA kernel
     // covers the rest.  HINT_B200_TF32_FWD=mma|tcgen05 forces one; HINT_MODE_TF32_MMA / HINT_MODE_TF32_TCGEN05 name them
     // explicitly (tests run both).
-    if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // the training kernel's mode: forward / inverse as in HINT_MODE_TF32
+    // The tcgen05 / TMEM machine of the training kernel also runs the transport alone (T3K_FORWARD / T3K_INVERSE programs):
+    // explicit with HINT_MODE_TF32_TC3, and the HINT_MODE_TF32 default for blocks the register-chained kernels do not cover
+    // (measured on the gas block: 2.5x the older tcgen05 forward kernel, which keeps the blocks outside this envelope).
+    const bool tc3_transport = hp->tc3f.ok && hp->tc3i.ok &&
+                               (mode == HINT_MODE_TF32_TC3 || (mode == HINT_MODE_TF32 && !hp->chain.ok && !dev_getenv("HINT_B200_TF32_FWD")));
+    if (tc3_transport) {
+        const T3Plan& t = rev ? hp->tc3i : hp->tc3f;
+        const DevTc3& dv = rev ? d->tc3i : d->tc3f;
+        CUDA_TRY(tc3_pack(t, dv, params, packed, st));
+        CUDA_TRY(tc3_launch_transport(t, dv, x, c, packed, z, logdet, (long long)B, st));
+        return HINT_OK;
+    }
+    if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // outside the transport envelope: forward / inverse as in HINT_MODE_TF32
     if (mode == HINT_MODE_TF32) {
         static const char* pref = dev_getenv("HINT_B200_TF32_FWD");
         const bool want_chain = pref ? std::strcmp(pref, "chain") == 0 : true;

@@ -209,17 +209,19 @@ static bool tmem_layout(T3Group& g) {
     return false;
 }
 static void group_dims(T3Group& g, int dc) {
-    g.KA = pad8(g.KX + dc + 1);
+    g.KA = pad8(g.KX + dc + 2);   // inputs, condition, and TWO ones columns: biases enter as hi + lo tf32 parts (kT3BiasLo)
     g.KD = pad8(g.OC);
     g.OW = pad16(g.OC);
     g.N2 = pad16(g.HP + 8);
-    g.N1 = pad16(g.KX + dc + 1);
+    g.N1 = pad16(g.KX + dc + 2);
     g.mtiles = (g.HP + 127) / 128;
 }
 
-void build_tc3_plan(const Plan& p, T3Plan& t) {
+void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
     t = T3Plan();
+    t.kind = kind;
     t.d = p.d; t.dc = p.dc; t.alpha = p.alpha;
+    const bool transport = kind != T3K_BACKWARD;
     auto fail = [&](const std::string& w) { t.ok = false; t.why = w; };
 
     // ---- groups: nodes of one depth, packed greedily while the group fits TMEM (and at most hp_cap hidden columns) ----
@@ -308,6 +310,10 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             OCmax = std::max(OCmax, g.OC); OWmax = std::max(OWmax, g.OW); mtmax = std::max(mtmax, g.mtiles);
         }
         t.op = OCmax | 1;
+        if (transport) {
+            if (layout(0, 4, 16384) || layout(0, 3, 16384) || layout(0, 2, 16384) || layout(0, 2, 8192)) { placed = true; break; }
+            continue;
+        }
         if (layout(3, 3, 16384) || layout(2, 3, 16384) || layout(2, 2, 16384) || layout(2, 3, 8192) || layout(2, 2, 8192)) { placed = true; break; }
     }
     if (!placed) return fail("the block's widest level does not fit shared memory");
@@ -315,7 +321,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
     // ---- partial-gradient layout + unpack map ----
     t.unpack_src.assign((size_t)p.n_params, -1);
     t.unpack_q4.assign((size_t)p.n_params, 0);
-    {
+    if (!transport) {
         int64_t o = 0;
         for (T3Group& g : t.groups) {
             const int rows = g.mtiles * 128;
@@ -358,7 +364,10 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
     const bool defer_flush = true;
     const int IMG_IN = 3, IMG_DOUT = 4;
     const int IMG_H1 = 0, IMG_H2 = 1, IMG_DH2 = t.n_imgs_hidden == 3 ? 2 : 1, IMG_DH1 = 1;
-    for (size_t gi = 0; gi < t.groups.size(); ++gi) {
+    // group order: backward and inverse visit the root level first (hint.py:85-88), forward the deepest level first (hint.py:70-73)
+    std::vector<size_t> gorder(t.groups.size());
+    for (size_t i = 0; i < gorder.size(); ++i) gorder[i] = kind == T3K_FORWARD ? gorder.size() - 1 - i : i;
+    for (size_t gi : gorder) {
         T3Group& g = t.groups[gi];
         const int nn = (int)g.nodes.size();
         const int P = g.tm_p, Q = g.tm_q;
@@ -375,6 +384,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
         }
         for (int q2 = 0; q2 < p.dc; ++q2) { in_src[g.KX + q2] = (p.d + q2); da_dst[g.KX + q2] = (p.d + q2); }
         in_src[g.KX + p.dc] = -2;
+        in_src[g.KX + p.dc + 1] = -2;
         const int tab_in = b.tab(in_src), tab_out = b.tab(out_x), tab_da = b.tab(da_dst);
         g.tab_nodes = b.tab(ntab);
 
@@ -387,6 +397,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
                     for (int m = 0; m < n.k; ++m) B.at(g.hoff[q] + j, g.xoff[q] + m) = (int32_t)(poffc(p, ni, net, 0, 0) + (int64_t)j * n.cin + m);
                     for (int q2 = 0; q2 < p.dc; ++q2) B.at(g.hoff[q] + j, g.KX + q2) = (int32_t)(poffc(p, ni, net, 0, 0) + (int64_t)j * n.cin + n.k + q2);
                     B.at(g.hoff[q] + j, g.KX + p.dc) = (int32_t)(poffc(p, ni, net, 0, 1) + j);
+                    B.at(g.hoff[q] + j, g.KX + p.dc + 1) = (int32_t)(poffc(p, ni, net, 0, 1) + j) | kT3BiasLo;
                 }
             }
             return B;
@@ -397,6 +408,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             for (int j = 0; j < n.h; ++j) {
                 for (int m = 0; m < n.h; ++m) B.at(j, m) = (int32_t)(poffc(p, ni, net, 1, 0) + (int64_t)j * n.h + m);
                 B.at(j, pad8(n.h)) = (int32_t)(poffc(p, ni, net, 1, 1) + j);
+                B.at(j, pad8(n.h) + 1) = (int32_t)(poffc(p, ni, net, 1, 1) + j) | kT3BiasLo;
             }
             return B;
         };
@@ -407,6 +419,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
                 for (int c = 0; c < n.cout; ++c) {
                     for (int m = 0; m < n.h; ++m) B.at(g.ooff[q] + c, g.hoff[q] + m) = (int32_t)(poffc(p, ni, net, 2, 0) + (int64_t)c * n.h + m);
                     B.at(g.ooff[q] + c, g.HP) = (int32_t)(poffc(p, ni, net, 2, 1) + c);
+                    B.at(g.ooff[q] + c, g.HP + 1) = (int32_t)(poffc(p, ni, net, 2, 1) + c) | kT3BiasLo;
                 }
             }
             return B;
@@ -525,6 +538,14 @@ void build_tc3_plan(const Plan& p, T3Plan& t) {
             T3Epi e{}; e.type = T3E_OUTS; e.a = g.tm_out; e.b = g.OC;
             Acc a; a.rd.push_back({R_TMEM, g.tm_out, g.tm_out + g.OC});
             b.push_epi(e, a);
+        }
+        if (transport) {
+            // ---- transport kernels: T forward, then the coupling itself (x_l <- e(s) x_l + t  or  (x_l - t) / e(s)) ----
+            fwd_chain(1, false, true);
+            T3Epi e{}; e.type = T3E_CPLF; e.a = g.tm_out; e.b = g.OC; e.c = tab_out; e.flags = kind == T3K_INVERSE ? 1 : 0;
+            Acc a; a.rd.push_back({R_TMEM, g.tm_out, g.tm_out + g.OC});
+            b.push_epi(e, a);
+            continue;
         }
         // ---- phase 2: T forward, coupling, T backward ----
         fwd_chain(1, true, true);

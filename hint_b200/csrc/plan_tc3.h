@@ -61,7 +61,10 @@ enum : int32_t {
     T3E_DHID,        // dgrad hidden layer: relu mask + rounding in place + image
     T3E_DA,          // input gradient: accumulate into the gradient state
     T3E_FLUSH,       // weight-gradient accumulator -> partial buffer
+    T3E_CPLF,        // forward / inverse kernels: the coupling itself (uses saved s, fresh t) + log-det accumulation
 };
+// kinds of program build_tc3_plan() generates
+enum : int { T3K_BACKWARD = 0, T3K_FORWARD = 1, T3K_INVERSE = 2 };
 // all fields 32-bit: the kernel reads a step as three 128-bit loads and never unpacks sub-word fields (see the note at
 // T3MmaWords in tc3_kernels.cuh)
 struct T3Epi {
@@ -77,6 +80,11 @@ enum : int32_t { T3H_IMG = 1, T3H_ONES = 2, T3H_IMG_ONES = 4 };
 enum : int32_t { T3D_MASK_TMEM = 1 };   // relu mask from TMEM (else from an image)
 // T3E_FLUSH kinds (field g): which column range of a lane's node is flushed
 enum : int32_t { T3F_W2 = 0, T3F_W1 = 1, T3F_W3 = 2 };
+
+// Biases enter the chain GEMMs as one extra K step against a constant block whose first TWO columns are 1: the packed operand
+// holds tf32(b) in the first and tf32(b - tf32(b)) in the second (pack_src entry | kT3BiasLo), so a bias keeps ~21 mantissa
+// bits instead of 10 - a rounded output-layer bias would shift t (and z) by up to 2^-11 |b| on its own.
+constexpr int32_t kT3BiasLo = 1 << 30;
 
 struct T3Chunk {
     uint32_t g_off;      // float offset in the packed weight buffer
@@ -103,6 +111,7 @@ struct T3Group {
 struct T3Plan {
     bool ok = false;
     std::string why;
+    int kind = T3K_BACKWARD;
     int d = 0, dc = 0;
     float alpha = 0.f;
     std::vector<T3Group> groups;          // root level first
@@ -122,7 +131,7 @@ struct T3Plan {
     int n_mma_signals = 0;
     // weights
     int64_t n_packed = 0;                // floats
-    std::vector<int32_t> pack_src;       // packed[i] = pack_src[i] < 0 ? 0 : tf32(params[pack_src[i]])
+    std::vector<int32_t> pack_src;       // packed[i] = pack_src[i] < 0 ? 0 : tf32(params[pack_src[i]]); | kT3BiasLo: the tf32 residual
     int64_t n_partial = 0;               // floats per CTA
     std::vector<int32_t> unpack_src;     // dparams[i] = sum over CTAs of partial[unpack_src[i]]
     std::vector<uint8_t> unpack_q4;      // 1: the parameter (a layer-3 bias) is the sum of 4 per-quadrant slots at stride 32
@@ -131,7 +140,10 @@ struct T3Plan {
 };
 
 // envelope: every group must fit TMEM (512 columns) and shared memory.  Never throws; on failure ok = false + why.
-void build_tc3_plan(const Plan& p, T3Plan& t);
+// kind = T3K_BACKWARD: the memory-free backward (training kernel).  T3K_FORWARD / T3K_INVERSE: the same machine running the
+// transport alone (hint.py:62-101): per group S chain -> s, T chain -> t, coupling step; no images, no accumulators, deepest
+// group first (forward, hint.py:70-73) or root first (inverse, hint.py:85-88).
+void build_tc3_plan(const Plan& p, T3Plan& t, int kind = T3K_BACKWARD);
 
 // SWIZZLE_128B K-major image: float index of (feature row r, sample s) in an image of `rows` allocated rows
 inline int t3_img_off(int r, int s, int rows) {

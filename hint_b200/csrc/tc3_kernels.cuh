@@ -41,6 +41,7 @@ struct T3Prog {
     int img_rows[kT3Imgs];
     int xp, op, d, dc, n_tab16;
     float alpha;
+    int kind;          // T3K_BACKWARD, or T3K_FORWARD / T3K_INVERSE: the transport alone (z = in, dx = out, x_rec = log-det out)
     float nll_scale;   // used when dz == NULL: dz = nll_scale * z, dlogdet = -nll_scale (fused NLL gradient, train_unconditional.py:128-132)
     const T3Epi* epis;
     const T3Chunk* chunks;
@@ -219,10 +220,17 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                 const int nx = rows * d;
                 const float* gz = z + row0 * d;
                 const float* gdz = dz + row0 * d;
-                for (int i = tid; i < 128 * d; i += 32 * kT3EpiWarps) {
-                    const int s = i / d, j = i - s * d;
-                    xs_all[s * P.xp + j] = i < nx ? __ldg(gz + i) : 0.f;
-                    gs_all[s * P.xp + j] = i < nx ? (dz ? __ldg(gdz + i) : P.nll_scale * __ldg(gz + i)) : 0.f;
+                if (P.kind != T3K_BACKWARD) {
+                    for (int i = tid; i < 128 * d; i += 32 * kT3EpiWarps) {
+                        const int s = i / d, j = i - s * d;
+                        xs_all[s * P.xp + j] = i < nx ? __ldg(gz + i) : 0.f;
+                    }
+                } else {
+                    for (int i = tid; i < 128 * d; i += 32 * kT3EpiWarps) {
+                        const int s = i / d, j = i - s * d;
+                        xs_all[s * P.xp + j] = i < nx ? __ldg(gz + i) : 0.f;
+                        gs_all[s * P.xp + j] = i < nx ? (dz ? __ldg(gdz + i) : P.nll_scale * __ldg(gz + i)) : 0.f;
+                    }
                 }
                 if (dc) {
                     const int nc = rows * dc;
@@ -234,7 +242,8 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                     }
                 }
             }
-            const float dJ = row < rows ? (dlogdet ? __ldg(dlogdet + row0 + row) : -P.nll_scale) : 0.f;
+            const float dJ = (P.kind == T3K_BACKWARD && row < rows) ? (dlogdet ? __ldg(dlogdet + row0 + row) : -P.nll_scale) : 0.f;
+            float Jacc = 0.f;   // transport kernels: log|det J| of this thread's sample (warpgroup 0)
             named_bar_sync(1, 32 * kT3EpiWarps);
             int waited = -1;
             for (int si = 0; si < P.n_epi; ++si, ++estep) {
@@ -303,7 +312,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                             finish16(q, v0);
                         }
                         if (wg == kWG - 1 && (e.flags & T3H_ONES)) {
-                            float o[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            float o[8] = {1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // two ones: bias hi + lo parts (kT3BiasLo)
                             st8(a0 + ncols, o);
                             if (e.flags & T3H_IMG_ONES) {
                                 unsigned char* ib = im + (uint32_t)(ncols >> 3) * 1024u;
@@ -390,6 +399,27 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                                     if ((lane & 3) == 0 && c0 + kcol < oc) {
                                         float* p1 = pq + c0 + kcol;
                                         if (first_tile) *p1 = a1; else atomicAdd(p1, a1);   // private slot: plain accumulation, issued as RED (no round trip)
+                                    }
+                                }
+                            }
+                        }
+                        break;
+                    }
+                    case T3E_CPLF: {   // the coupling of the transport kernels (hint.py:79-84): s saved by OUTS, t fresh in TMEM
+                        if (wg == 0) {
+                            const bool inv = e.flags != 0;
+                            for (int c0 = 0; c0 < e.b; c0 += 8) {
+                                float tv[8];
+                                ld8(lane_base + (uint32_t)(e.a + c0), tv);
+                                wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int col = c0 + j;
+                                    if (col < e.b) {
+                                        const int xc = s_tab[e.c + col];
+                                        const float la = alpha * t3_atan(OS[col]);
+                                        if (!inv) { XS[xc] = fmaf(t3_exp(la), XS[xc], tv[j]); Jacc += la; }
+                                        else { XS[xc] = (XS[xc] - tv[j]) * t3_exp(-la); Jacc -= la; }
                                     }
                                 }
                             }
@@ -546,12 +576,19 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                 const float* xs_all = reinterpret_cast<const float*>(smem + P.sm_xs);
                 const float* gs_all = reinterpret_cast<const float*>(smem + P.sm_gs);
                 const int nx = rows * d;
+                if (P.kind != T3K_BACKWARD) {
+                    for (int i = tid; i < nx; i += 32 * kT3EpiWarps) {
+                        const int s = i / d, j = i - s * d;
+                        dx[row0 * d + i] = xs_all[s * P.xp + j];
+                    }
+                    if (wg == 0 && row < rows) x_rec[row0 + row] = Jacc;
+                } else
                 for (int i = tid; i < nx; i += 32 * kT3EpiWarps) {
                     const int s = i / d, j = i - s * d;
                     dx[row0 * d + i] = gs_all[s * P.xp + j];
                     if (x_rec) x_rec[row0 * d + i] = xs_all[s * P.xp + j];
                 }
-                if (dc && dcond) {
+                if (dc && dcond && P.kind == T3K_BACKWARD) {
                     const int nc = rows * dc;
                     for (int i = tid; i < nc; i += 32 * kT3EpiWarps) {
                         const int s = i / dc, j = i - s * dc;
@@ -604,7 +641,10 @@ __global__ void hint_tc3_reduce_kernel(const int* __restrict__ dst, const float*
 __global__ void hint_tc3_pack_kernel(const int* __restrict__ src, const float* __restrict__ params, float* __restrict__ packed, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int s = src[i];
-        packed[i] = s < 0 ? 0.f : tc::to_tf32(params[s]);
+        if (s < 0) { packed[i] = 0.f; continue; }
+        const float v = params[s & ~kT3BiasLo];
+        const float hi = tc::to_tf32(v);
+        packed[i] = (s & kT3BiasLo) ? tc::to_tf32(v - hi) : hi;
     }
 }
 

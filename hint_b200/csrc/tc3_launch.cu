@@ -30,7 +30,8 @@ cudaError_t tc3_setup(const T3Plan& t, int num_sms, DevTc3& d) {
     if ((e = upload(&d.tab16, t.tab16)) != cudaSuccess) return e;
     if ((e = upload(&d.pack_src, t.pack_src)) != cudaSuccess) return e;
     std::vector<int32_t> dst((size_t)t.n_partial, -1);
-    for (size_t i = 0; i < t.unpack_src.size(); ++i) dst[(size_t)t.unpack_src[i]] = (int32_t)i | (t.unpack_q4[i] ? (1 << 30) : 0);
+    if (t.kind == T3K_BACKWARD)
+        for (size_t i = 0; i < t.unpack_src.size(); ++i) dst[(size_t)t.unpack_src[i]] = (int32_t)i | (t.unpack_q4[i] ? (1 << 30) : 0);
     if ((e = upload(&d.part_dst, dst)) != cudaSuccess) return e;
     T3Prog* P = new T3Prog();
     std::memset(P, 0, sizeof(T3Prog));
@@ -40,11 +41,13 @@ cudaError_t tc3_setup(const T3Plan& t, int num_sms, DevTc3& d) {
     for (int i = 0; i < kT3Imgs; ++i) { P->sm_img[i] = t.sm_img[i]; P->img_rows[i] = t.img_rows[i]; }
     P->xp = t.xp; P->op = t.op; P->d = t.d; P->dc = t.dc; P->n_tab16 = (int)t.tab16.size();
     P->alpha = t.alpha;
+    P->kind = t.kind;
     P->epis = d.epis; P->chunks = d.chunks; P->tab16 = d.tab16;
     for (size_t i = 0; i < t.mmas.size(); ++i) P->mmas[i] = t3_pack_mma(t.mmas[i]);
     d.prog = P;
     d.num_sms = num_sms;
-    return cudaFuncSetAttribute((const void*)hint_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem_bytes);
+    // the attribute is per function, and several plans (backward, forward, inverse; every block) share the kernel: always the maximum
+    return cudaFuncSetAttribute((const void*)hint_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
 }
 
 void tc3_free(DevTc3& d) {
@@ -85,6 +88,14 @@ cudaError_t tc3_launch_bwd(const T3Plan& t, const DevTc3& d, int grid, const flo
     return cudaGetLastError();
 }
 
+
+cudaError_t tc3_launch_transport(const T3Plan& t, const DevTc3& d, const float* x, const float* cond, const float* packed, float* z,
+                                 float* logdet, long long B, cudaStream_t st) {
+    const int grid = tc3_bwd_ctas(d, B);
+    hint_tc3_bwd_kernel<<<grid, kT3Threads, t.smem_bytes, st>>>(*d.prog, x, cond, packed, nullptr, nullptr, logdet, z, nullptr, nullptr, 0, B,
+                                                                nullptr, nullptr); HINT_LAUNCHED();
+    return cudaGetLastError();
+}
 
 // Developer aid (tests/cuda/dbg_tc3.py): run ONE tile, stop after `n_epi_limit` epilogue steps and dump TMEM + shared memory.
 cudaError_t tc3_debug_run(const T3Plan& t, const DevTc3& d, int n_epi_limit, const float* z, const float* cond, const float* packed,

@@ -27,6 +27,10 @@ cudaError_t tc3_launch_bwd(const T3Plan& t, const DevTc3& d, int grid, const flo
                            const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc, float* partials,
                            float* dparams, long long B, cudaStream_t st, long long* prof = nullptr, float nll_scale = 0.f);
 
+// forward / inverse transport with a T3K_FORWARD / T3K_INVERSE plan: z [B,d], logdet [B]
+cudaError_t tc3_launch_transport(const T3Plan& t, const DevTc3& d, const float* x, const float* cond, const float* packed, float* z,
+                                 float* logdet, long long B, cudaStream_t st);
+
 // developer aid: one tile, stop after n_epi_limit epilogue steps, dump TMEM [128][512] + raw shared memory (floats)
 cudaError_t tc3_debug_run(const T3Plan& t, const DevTc3& d, int n_epi_limit, const float* z, const float* cond, const float* packed,
                           const float* dz, const float* dlogdet, float* x_rec, float* dx, float* dc, float* partials, long long B,

@@ -29,21 +29,23 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                    int min_split_size, const float* params, const float* z, const float* c, const float* dz,
                    const float* dJ, long long B, int lazy, int tf32, float* xrec, float* dx, float* dcond,
                    float* dparams, long long* info, int n_epi_limit, float* tmem_out, float* img_out, float* xs_out, float* gs_out,
-                   float* os_out) {
+                   float* os_out, int kind = T3K_BACKWARD, float* logdet_out = nullptr) {
     Plan p;
     int code = 0;
     std::string err = build_plan(p, d, dc, c_internal, n_internal, clamp, max_splits, min_split_size, 0, &code);
     if (!err.empty()) return code ? code : 1;
     T3Plan t;
-    build_tc3_plan(p, t);
+    build_tc3_plan(p, t, kind);
     info[0] = t.ok; info[1] = (long long)t.groups.size(); info[2] = (long long)t.mmas.size(); info[3] = (long long)t.epis.size();
     info[4] = (long long)t.chunks.size(); info[5] = t.n_packed; info[6] = t.smem_bytes; info[7] = t.n_partial;
     info[8] = t.n_mma_instr; info[9] = t.tensor_cycles; info[10] = t.n_imgs_hidden; info[11] = t.n_slots;
     if (!t.ok) return 200;
     std::vector<float> W((size_t)t.n_packed);
     for (long long i = 0; i < t.n_packed; ++i) {
-        float v = t.pack_src[i] < 0 ? 0.f : params[t.pack_src[i]];
-        W[i] = tf32 ? rna_tf32(v) : v;
+        if (t.pack_src[i] < 0) { W[i] = 0.f; continue; }
+        const float v = params[t.pack_src[i] & ~kT3BiasLo];
+        const float hi = tf32 ? rna_tf32(v) : v;
+        W[i] = (t.pack_src[i] & kT3BiasLo) ? (tf32 ? rna_tf32(v - hi) : 0.f) : hi;
     }
     auto rt = [&](float v) { return tf32 ? rna_tf32(v) : v; };
     auto opnd = [&](float v) { return tf32 ? trunc_tf32(v) : v; };   // what the tensor core reads
@@ -122,13 +124,14 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
             for (int j = 0; j < nd; ++j) {
                 float xv = 0.f, gv = 0.f;
                 if (s < rows) {
-                    if (j < p.d) { xv = z[(row0 + s) * p.d + j]; gv = dz[(row0 + s) * p.d + j]; }
+                    if (j < p.d) { xv = z[(row0 + s) * p.d + j]; gv = dz ? dz[(row0 + s) * p.d + j] : 0.f; }
                     else xv = c[(row0 + s) * p.dc + (j - p.d)];
                 }
                 XS[(size_t)s * xp + j] = xv; GS[(size_t)s * xp + j] = gv;
             }
-            DJ[s] = s < rows ? dJ[row0 + s] : 0.f;
+            DJ[s] = (s < rows && dJ) ? dJ[row0 + s] : 0.f;
         }
+        std::vector<float> JA(128, 0.f);   // transport kernels: log-det accumulators
         int pm = 0, pe = 0, done_sig = -1, issued_upto = 0;   // records [issued_upto, pm) are issued but not executed (lazy)
         auto run_queued = [&](int upto_sig) {
             while (issued_upto < pm && sig[issued_upto] <= upto_sig) exec_mma(issued_upto++);
@@ -151,8 +154,8 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                             tm(s, e.a + col) = v;
                             if (e.flags & T3H_IMG) im(e.c, col, s) = v;
                         }
-                        if (e.flags & T3H_ONES) for (int q = 0; q < 8; ++q) tm(s, e.a + e.b + q) = q == 0 ? 1.f : 0.f;
-                        if (e.flags & T3H_IMG_ONES) for (int q = 0; q < 8; ++q) im(e.c, e.b + q, s) = q == 0 ? 1.f : 0.f;
+                        if (e.flags & T3H_ONES) for (int q = 0; q < 8; ++q) tm(s, e.a + e.b + q) = q < 2 ? 1.f : 0.f;
+                        if (e.flags & T3H_IMG_ONES) for (int q = 0; q < 8; ++q) im(e.c, e.b + q, s) = q < 2 ? 1.f : 0.f;
                     }
                     break;
                 case T3E_OUTS:
@@ -178,6 +181,17 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                         }
                     }
                     for (int s = 0; s < 128; ++s) for (int col = e.b; col < e.e; ++col) tm(s, e.d + col) = 0.f;
+                    break;
+                case T3E_CPLF:
+                    for (int col = 0; col < e.b; ++col) {
+                        const int xc = tb[e.c + col];
+                        for (int s = 0; s < 128; ++s) {
+                            const float la = alpha * atanf(OS[(size_t)s * op + col]), tv = tm(s, e.a + col);
+                            float& xr = XS[(size_t)s * xp + xc];
+                            if (!e.flags) { xr = expf(la) * xr + tv; JA[s] += la; }
+                            else { xr = (xr - tv) / expf(la); JA[s] -= la; }
+                        }
+                    }
                     break;
                 case T3E_DS:
                     for (int col = 0; col < e.b; ++col) {
@@ -252,6 +266,11 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
         if (lazy) run_queued(1 << 30);
         (void)done_sig;
         for (int s = 0; s < rows; ++s) {
+            if (kind != T3K_BACKWARD) {
+                for (int j = 0; j < p.d; ++j) dx[(row0 + s) * p.d + j] = XS[(size_t)s * xp + j];
+                logdet_out[row0 + s] = JA[s];
+                continue;
+            }
             for (int j = 0; j < p.d; ++j) {
                 dx[(row0 + s) * p.d + j] = GS[(size_t)s * xp + j];
                 if (xrec) xrec[(row0 + s) * p.d + j] = XS[(size_t)s * xp + j];
@@ -259,6 +278,7 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
             for (int j = 0; j < p.dc; ++j) dcond[(row0 + s) * p.dc + j] = GS[(size_t)s * xp + p.d + j];
         }
     }
+    if (kind != T3K_BACKWARD) return 0;
     for (long long i = 0; i < p.n_params; ++i) {
         double v = part[(size_t)t.unpack_src[i]];
         if (t.unpack_q4[(size_t)i]) for (int q = 1; q < 4; ++q) v += part[(size_t)t.unpack_src[i] + 32 * q];
@@ -279,6 +299,14 @@ extern "C" int emul_tc3_backward(int d, int dc, const int* c_internal, int n_int
                                  float* dparams, long long* info) {
     return run_tc3(d, dc, c_internal, n_internal, clamp, max_splits, min_split_size, params, z, c, dz, dJ, B, lazy, tf32, xrec, dx, dcond,
                    dparams, info, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// forward (rev = 0) / inverse (rev = 1) transport through the T3K_FORWARD / T3K_INVERSE programs
+extern "C" int emul_tc3_transport(int d, int dc, const int* c_internal, int n_internal, double clamp, int max_splits, int min_split_size,
+                                  const float* params, const float* x, const float* c, long long B, int rev, int lazy, int tf32,
+                                  float* z, float* logdet, long long* info) {
+    return run_tc3(d, dc, c_internal, n_internal, clamp, max_splits, min_split_size, params, x, c, nullptr, nullptr, B, lazy, tf32, nullptr, z,
+                   nullptr, nullptr, info, 0, nullptr, nullptr, nullptr, nullptr, nullptr, rev ? T3K_INVERSE : T3K_FORWARD, logdet);
 }
 
 // developer aid: ONE tile (B <= 128), stop after n_epi_limit epilogue steps, dump TMEM [128][512], the 5 images (rows*128 floats

@@ -25,6 +25,7 @@ def lib():
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB] + SRC, check=True)
         _lib = ctypes.CDLL(LIB)
         _lib.emul_tc3_backward.restype = ctypes.c_int
+        _lib.emul_tc3_transport.restype = ctypes.c_int
     return _lib
 
 
@@ -53,3 +54,24 @@ def backward(d, dc, c_internal, clamp, max_splits, min_split_size, params, z, c,
     if rc != 0:
         raise RuntimeError(f"emul_tc3_backward failed with code {rc} ({'deadlock in the inferred waits' if rc == 400 else 'internal'})")
     return dict(xrec=xrec, dx=dx, dc=dcond[:, :dc] if dc else None, dparams=dparams, info=inf)
+
+
+def transport(d, dc, c_internal, clamp, max_splits, min_split_size, params, x, c, rev=False, lazy=False, tf32=False):
+    """Forward (rev=False) / inverse transport through the tcgen05 machine's T3K_FORWARD / T3K_INVERSE programs -> dict(z, J, info)."""
+    B = x.shape[0]
+    ci = np.asarray(list(c_internal), dtype=np.int32)
+    f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    params, x, c = f(params), f(x), f(c)
+    z = np.full((B, d), np.nan, np.float32)
+    J = np.full((B,), np.nan, np.float32)
+    info = np.zeros(16, np.int64)
+    rc = lib().emul_tc3_transport(ctypes.c_int(d), ctypes.c_int(dc), _p(ci, ctypes.c_int), ctypes.c_int(len(ci)), ctypes.c_double(clamp),
+                                  ctypes.c_int(max_splits), ctypes.c_int(min_split_size), _p(params), _p(x), _p(c), ctypes.c_longlong(B),
+                                  ctypes.c_int(1 if rev else 0), ctypes.c_int(1 if lazy else 0), ctypes.c_int(1 if tf32 else 0), _p(z), _p(J),
+                                  _p(info, ctypes.c_longlong))
+    inf = dict(zip(INFO, (int(v) for v in info)))
+    if rc == 200:
+        raise LookupError("outside the tc3 envelope")
+    if rc != 0:
+        raise RuntimeError(f"emul_tc3_transport failed with code {rc}")
+    return dict(z=z, J=J, info=inf)

@@ -124,3 +124,24 @@ def test_random_trees_against_the_oracle(seed):
     assert _l2(out["dx"], dx_ref.numpy()) < 2e-3 and _l2(out["dparams"], dp_ref.numpy()) < 2e-3
     if dc:
         assert _l2(out["dc"], dc_ref.numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("lazy", [False, True], ids=["eager", "lazy"])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_transport_programs_reproduce_reference_forward_and_inverse(name, lazy):
+    """The same machine running the transport alone (T3K_FORWARD: deepest level first, T3K_INVERSE: root first; S chain, T chain,
+    coupling step per group): z, log-det and the inverse against the golden vectors of the real module, several tiles incl. a
+    ragged one."""
+    g = load_golden(name)
+    args = _args(g)
+    reps = 3
+    x = np.tile(g["x"], (reps, 1))[:-1]
+    c = None if g.get("c") is None else np.tile(g["c"], (reps, 1))[:-1]
+    out = emul_tc3_lib.transport(*args, x, c, rev=False, lazy=lazy)
+    zref, Jref = np.tile(g["z64"], (reps, 1))[:-1], np.tile(g["J64"], reps)[:-1]
+    assert np.abs(out["z"] - zref).max() < 2e-5 * max(1.0, np.abs(zref).max())
+    assert np.abs(out["J"] - Jref).max() < 2e-5 * max(1.0, np.abs(Jref).max())
+    inv = emul_tc3_lib.transport(*args, x, c, rev=True, lazy=lazy)
+    xiref, Jiref = np.tile(g["xinv64"], (reps, 1))[:-1], np.tile(g["Jinv64"], reps)[:-1]
+    assert np.abs(inv["z"] - xiref).max() < 2e-5 * max(1.0, np.abs(xiref).max())
+    assert np.abs(inv["J"] - Jiref).max() < 2e-5 * max(1.0, np.abs(Jiref).max())

@@ -33,7 +33,7 @@ def _split_c(c, dims_c, dev):
     return out
 
 
-@pytest.mark.parametrize("mode", ["tf32", "tf32_chain", "tf32_mma", "tf32_tcgen05"])
+@pytest.mark.parametrize("mode", ["tf32", "tf32_chain", "tf32_mma", "tf32_tcgen05", "tf32_tc3"])
 def test_golden_forward_inverse_tf32(golden, mode):
     import hint_b200
     from hint_b200 import HierarchicalAffineCouplingBlock
@@ -90,7 +90,7 @@ def _report(tag, **errs):
         pass
 
 
-@pytest.mark.parametrize("mode", ["tf32", "tf32_chain", "tf32_mma", "tf32_tcgen05"])
+@pytest.mark.parametrize("mode", ["tf32", "tf32_chain", "tf32_mma", "tf32_tcgen05", "tf32_tc3"])
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c[0])
 def test_reference_configs_tf32(cfg, mode):
     name, d, dc, ci, ms, B = cfg
