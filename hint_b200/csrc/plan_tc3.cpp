@@ -17,6 +17,7 @@ namespace {
 constexpr int kTmemCols = 512;
 constexpr int kHpMaxMulti = 128;   // hidden columns of a multi-node group (one M tile of the weight-gradient GEMMs)
 constexpr int kHpMaxSingle = 160;  // a single node may be wider (second M tile)
+constexpr int kHpMaxTransport = 232; // forward / inverse programs: 2 (h + 8) + operands <= 512 columns, MMA N <= 256
 constexpr int kKaMax = 32, kOwMax = 32;
 
 enum ResKind { R_TMEM = 0, R_IMG0 = 1 /* .. R_IMG0 + kT3Imgs - 1 */ };
@@ -190,10 +191,19 @@ int pad16(int v) { return (v + 15) & ~15; }
 
 }  // namespace
 
-// TMEM map of one group; false if it needs more than 512 columns
-static bool tmem_layout(T3Group& g) {
+// TMEM map of one group; false if it needs more than 512 columns.  The transport kernels need the two hidden buffers and the
+// small operands only (no accumulators), which admits single nodes up to h = 232.
+static bool tmem_layout(T3Group& g, bool transport) {
     const int PW = g.HP + 8;
     int c = 0;
+    if (transport) {
+        g.tm_p = c; c += PW;
+        g.tm_q = c; c += PW;
+        g.tm_ain = c; c += g.KA;
+        g.tm_out = c; c += g.OW;
+        g.tm_acc2 = g.tm_dout = g.tm_da = g.tm_acc1 = g.tm_acc3 = 0;
+        return c <= kTmemCols;
+    }
     g.tm_p = c; c += PW;
     g.tm_q = c; c += PW;
     g.tm_acc2 = c; c += g.N2;
@@ -233,14 +243,14 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
                 const auto& n = p.nodes[i];
                 if (n.depth != depth) continue;
                 const int hp = pad16(n.h);
-                if (hp > kHpMaxSingle) { fail("hidden width " + std::to_string(n.h) + " exceeds the TMEM budget of the tcgen05 training kernel"); return false; }
+                if (hp > (transport ? kHpMaxTransport : kHpMaxSingle)) { fail("hidden width " + std::to_string(n.h) + " exceeds the TMEM budget of the tcgen05 training kernel"); return false; }
                 T3Group trial = g;
                 trial.nodes.push_back(i);
                 trial.hoff.push_back(g.HP); trial.xoff.push_back(g.KX); trial.ooff.push_back(g.OC);
                 trial.HP += hp; trial.KX += n.k; trial.OC += n.cout;
                 group_dims(trial, p.dc);
                 const bool fits = trial.nodes.size() == 1 ||
-                                  (trial.HP <= hp_cap && trial.KA <= kKaMax && trial.OW <= kOwMax && (int)trial.nodes.size() <= 16 && tmem_layout(trial));
+                                  (trial.HP <= hp_cap && trial.KA <= kKaMax && trial.OW <= kOwMax && (int)trial.nodes.size() <= 16 && tmem_layout(trial, transport));
                 if (!fits) {
                     t.groups.push_back(g);
                     trial = T3Group();
@@ -256,7 +266,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         for (T3Group& g : t.groups) {
             group_dims(g, p.dc);
             if (g.KA > kKaMax || g.OW > kOwMax) { fail("a node's input/output width exceeds the tcgen05 training kernel's envelope"); return false; }
-            if (!tmem_layout(g)) { fail("a tree level does not fit the 512 TMEM columns"); return false; }
+            if (!tmem_layout(g, transport)) { fail("a tree level does not fit the 512 TMEM columns"); return false; }
         }
         return true;
     };

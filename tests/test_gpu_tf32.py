@@ -73,6 +73,9 @@ CONFIGS = [
     ("plus_hint_4_3", 100, 0, [314, 157, 78, 39], 3, 500),
     ("plus_hint_4_full", 100, 0, [263, 131, 65, 32, 32], -1, 300),
     ("plus_cond_recursive_4", 100, 4, [267, 133, 66], -1, 300),
+    # the hint_4 UCI variants: single nodes of h = 200 / 184 (tcgen05 transport programs up to h = 232; backward: interpreter)
+    ("power_hint_4", 6, 0, [200, 100, 50, 25], -1, 700),
+    ("gas_hint_4", 8, 0, [184, 92, 46, 23], -1, 700),
 ]
 
 
