@@ -226,13 +226,13 @@ def measure_tf32_peak(torch, dev):
 
 
 def bwd_kernel_name(plan, mode):
-    if mode == "fp32" or mode == "tf32_tcgen05":
+    if mode == "fp32":
         return "hint_bwd_fp32_kernel"
     if mode == "tf32x3":
         return "hint_bwd_mma_kernel<TM,3xTF32>"
     if mode in ("tf32", "tf32_chain") and plan.mode_supported("tf32_chain"):
         return "hint_bwd_chain_kernel<MT=1,NW=4> (register-chained warp-MMA)"
-    if mode in ("tf32", "tf32_tc3") and plan.mode_supported("tf32_tc3"):
+    if mode in ("tf32", "tf32_tc3", "tf32_tcgen05") and plan.mode_supported("tf32_tc3"):
         return "hint_tc3_bwd_kernel (tcgen05 / TMEM)"
     return "hint_bwd_mma_kernel<TM,TF32>"
 

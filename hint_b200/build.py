@@ -19,7 +19,6 @@ HDR_API = os.path.join("..", "..", "include", "hint_b200.h")
 # translation unit -> headers it depends on
 UNITS = {
     "plan.cpp": ["plan.h", HDR_API],
-    "plan_tc.cpp": ["plan.h", "plan_tc.h", HDR_API],
     "plan_mma.cpp": ["plan.h", "plan_mma.h", HDR_API],
     "plan_chain.cpp": ["plan.h", "plan_chain.h", HDR_API],
     "plan_tc3.cpp": ["plan.h", "plan_tc3.h", HDR_API],
@@ -28,7 +27,7 @@ UNITS = {
     "mma_launch.cu": ["launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "mma_kernels.cuh", HDR_API],
     "train_ops.cu": ["train_ops.h", "launch_count.h", HDR_API],
     "householder.cu": ["householder.h", "launch_count.h", HDR_API],
-    "capi.cu": ["train_ops.h", "householder.h", "launch_count.h", "plan.h", "plan_tc.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", "tc2_kernels.cuh",
+    "capi.cu": ["train_ops.h", "householder.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 
                 "simt_phases.cuh", "simt_kernels.cuh", HDR_API],
 }
 NVCC_FLAGS = ["-O3", "-std=c++17", "-DHINT_MMA_MINB=2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -12,7 +12,6 @@
 
 #include "launch_count.h"
 #include "plan.h"
-#include "plan_tc.h"
 #include "plan_mma.h"
 #include "mma_launch.h"
 #include "plan_chain.h"
@@ -22,7 +21,6 @@
 #include "train_ops.h"
 #include "householder.h"
 #include "simt_kernels.cuh"
-#include "tc2_kernels.cuh"
 
 using namespace hint;
 
@@ -65,18 +63,8 @@ struct DevSchedule {
     int max_ctas = 0;  // SMs x occupancy
 };
 
-struct DevTc {
-    TcStage* stages = nullptr;
-    TcOp* ops = nullptr;
-    TcChunk* chunks = nullptr;
-    TcFinal* fins = nullptr;
-    int* xlog = nullptr;
-    int* pack_src = nullptr;
-};
-
 struct DevPlan {
     DevSchedule fwd, bwd;
-    DevTc tc;
     DevMma mma;
     DevChain chain;
     DevTc3 tc3, tc3f, tc3i;   // training kernel; the same machine running the forward / inverse transport
@@ -92,8 +80,6 @@ struct hint_plan {
     MmaPlan mma;
     ChainPlan chain;
     T3Plan tc3, tc3f, tc3i;
-    TcSchedule tc;
-    T2Host tc2;
     std::mutex mu;
     std::map<int, DevPlan> dev;  // per CUDA device ordinal
 };
@@ -168,16 +154,6 @@ int get_dev(hint_plan* hp, DevPlan** out) {
     if (hp->tc3f.ok && hp->tc3i.ok) {
         CUDA_TRY(tc3_setup(hp->tc3f, d.num_sms, d.tc3f));
         CUDA_TRY(tc3_setup(hp->tc3i, d.num_sms, d.tc3i));
-    }
-    if (hp->tc.ok) {
-        CUDA_TRY(upload(&d.tc.stages, hp->tc.stages));
-        CUDA_TRY(upload(&d.tc.ops, hp->tc.ops));
-        CUDA_TRY(upload(&d.tc.chunks, hp->tc.chunks));
-        CUDA_TRY(upload(&d.tc.fins, hp->tc.fins));
-        CUDA_TRY(upload(&d.tc.xlog, hp->tc.xlog));
-        CUDA_TRY(upload(&d.tc.pack_src, hp->tc.pack_src));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)hint_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     }
     auto res = hp->dev.emplace(dev, d);
     *out = &res.first->second;
@@ -291,8 +267,6 @@ int hint_plan_create(int32_t d, int32_t dc, const int32_t* c_internal, int32_t n
     build_tc3_plan(hp->p, hp->tc3);
     build_tc3_plan(hp->p, hp->tc3f, T3K_FORWARD);
     build_tc3_plan(hp->p, hp->tc3i, T3K_INVERSE);
-    build_tc_schedule(hp->p, hp->tc);
-    build_tc2_program(hp->p, hp->tc, hp->tc2);
     *out = hp;
     return HINT_OK;
 }
@@ -313,7 +287,6 @@ void hint_plan_destroy(hint_plan_t* hp) {
         tc3_free(d.tc3);
         tc3_free(d.tc3f);
         tc3_free(d.tc3i);
-        cudaFree(d.tc.stages); cudaFree(d.tc.ops); cudaFree(d.tc.chunks); cudaFree(d.tc.fins); cudaFree(d.tc.xlog); cudaFree(d.tc.pack_src);
         cudaSetDevice(cur);
     }
     delete hp;
@@ -348,9 +321,8 @@ int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
     switch (mode) {
         case HINT_MODE_FP32: return 1;
         case HINT_MODE_TF32: case HINT_MODE_TF32X3: case HINT_MODE_TF32_MMA: return hp->mma.ok ? 1 : 0;
-        case HINT_MODE_TF32_TCGEN05: return (hp->tc.ok && hp->tc2.ok) ? 1 : 0;
         case HINT_MODE_TF32_CHAIN: return (hp->chain.ok && hp->mma.ok) ? 1 : 0;
-        case HINT_MODE_TF32_TC3: return (hp->tc3.ok && hp->mma.ok) ? 1 : 0;
+        case HINT_MODE_TF32_TC3: case HINT_MODE_TF32_TCGEN05: return (hp->tc3.ok && hp->mma.ok) ? 1 : 0;
     }
     return 0;
 }
@@ -358,7 +330,7 @@ int32_t hint_plan_mode_supported(const hint_plan_t* hp, int32_t mode) {
 size_t hint_workspace_bytes(const hint_plan_t* hp_c, int64_t B, int32_t which) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
     if (!hp || B < 0) { fail(HINT_ERR_INVALID, "bad plan or batch"); return 0; }
-    size_t bytes = align256((size_t)std::max<long long>(hp->p.n_packed, hp->tc.ok ? hp->tc.n_packed : 0) * 4);
+    size_t bytes = align256((size_t)hp->p.n_packed * 4);
     if (hp->mma.ok) bytes = std::max(bytes, mma_packed_bytes(hp->mma));
     if (hp->chain.ok) bytes = std::max(bytes, align256((size_t)hp->chain.n_packed * 4));
     if (hp->tc3.ok) bytes = std::max(bytes, align256((size_t)hp->tc3.n_packed * 4));
@@ -381,16 +353,15 @@ static int check_common(const hint_plan* hp, const float* x, const float* c, con
     if (mode != HINT_MODE_FP32 && mode != HINT_MODE_TF32 && mode != HINT_MODE_TF32X3 && mode != HINT_MODE_TF32_TCGEN05 &&
         mode != HINT_MODE_TF32_MMA && mode != HINT_MODE_TF32_CHAIN && mode != HINT_MODE_TF32_TC3)
         return fail(HINT_ERR_INVALID, "unknown mode");
+    if (mode == HINT_MODE_TF32_TCGEN05) mode = HINT_MODE_TF32_TC3;   // one tcgen05 / TMEM machine: the older name is an alias
     if (mode == HINT_MODE_TF32_TC3 && !hp->tc3.ok)
-        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the tcgen05 training kernel's envelope: " + hp->tc3.why);
+        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the tcgen05 kernels' envelope: " + hp->tc3.why);
     if (mode == HINT_MODE_TF32_TC3) mode = HINT_MODE_TF32;   // forward / inverse: the TF32 default
     if (mode == HINT_MODE_TF32_CHAIN && !hp->chain.ok)
         return fail(HINT_ERR_UNSUPPORTED, "this block is outside the register-chained kernels' envelope: " + hp->chain.why);
     if (mode == HINT_MODE_TF32_CHAIN) mode = HINT_MODE_TF32_MMA;   // same requirements otherwise
     if ((mode == HINT_MODE_TF32 || mode == HINT_MODE_TF32X3 || mode == HINT_MODE_TF32_MMA) && !hp->mma.ok)
         return fail(HINT_ERR_UNSUPPORTED, "this block is outside the warp-MMA kernels' envelope: " + hp->mma.why);
-    if (mode == HINT_MODE_TF32_TCGEN05 && !hp->tc.ok)
-        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the TF32 (tcgen05) kernel's envelope: " + hp->tc.why);
     if (B > 0 && (!x || !params)) return fail(HINT_ERR_INVALID, "NULL input pointer");
     if (B > 0 && hp->p.dc > 0 && !c) return fail(HINT_ERR_INVALID, "plan has a condition input but c is NULL");
     if (!aligned16(x) || !aligned16(c) || !aligned16(params)) return fail(HINT_ERR_INVALID, "pointers must be 16-byte aligned");
@@ -419,6 +390,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     // The tcgen05 / TMEM machine of the training kernel also runs the transport alone (T3K_FORWARD / T3K_INVERSE programs):
     // explicit with HINT_MODE_TF32_TC3, and the HINT_MODE_TF32 default for blocks the register-chained kernels do not cover
     // (measured on the gas block: 2.5x the older tcgen05 forward kernel, which keeps the blocks outside this envelope).
+    if (mode == HINT_MODE_TF32_TCGEN05) mode = HINT_MODE_TF32_TC3;
     const bool tc3_transport = hp->tc3f.ok && hp->tc3i.ok &&
                                (mode == HINT_MODE_TF32_TC3 || (mode == HINT_MODE_TF32 && !hp->chain.ok && !dev_getenv("HINT_B200_TF32_FWD")));
     if (tc3_transport) {
@@ -432,9 +404,7 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
     if (mode == HINT_MODE_TF32) {
         static const char* pref = dev_getenv("HINT_B200_TF32_FWD");
         const bool want_chain = pref ? std::strcmp(pref, "chain") == 0 : true;
-        const bool want_tc = pref ? std::strcmp(pref, "tcgen05") == 0 : true;
-        mode = (want_chain && hp->chain.ok) ? HINT_MODE_TF32_CHAIN
-               : (want_tc && hp->tc.ok && hp->tc2.ok) ? HINT_MODE_TF32_TCGEN05 : HINT_MODE_TF32_MMA;
+        mode = (want_chain && hp->chain.ok) ? HINT_MODE_TF32_CHAIN : HINT_MODE_TF32_MMA;
     }
     if (mode == HINT_MODE_TF32_CHAIN) {
         CUDA_TRY(chain_pack(hp->chain, d->chain, params, packed, st));
@@ -448,40 +418,6 @@ int hint_forward(const hint_plan_t* hp_c, const float* x, const float* c, const 
         CUDA_TRY(mma_pack(hp->mma, d->mma, params, hi, x3 ? lo : nullptr, st));
         CUDA_TRY(mma_launch_fwd(hp->p, hp->mma, d->mma, x3, x, c, hi, lo, z, logdet, (long long)B, rev ? 1 : 0, st));
         return HINT_OK;
-    }
-    if (mode == HINT_MODE_TF32_TCGEN05) {
-        const TcSchedule& t = hp->tc;
-        {
-            const int threads = 256;
-            const int blocks = (int)std::min<long long>((t.n_packed + threads - 1) / threads, 148 * 8);
-            hint_pack_tc_kernel<<<blocks, threads, 0, st>>>(d->tc.pack_src, params, packed, t.n_packed, t.n_weight_floats); HINT_LAUNCHED();
-            CUDA_TRY(cudaGetLastError());
-        }
-        if (hp->tc2.ok) {
-            const long long ntiles = (B + 127) / 128;
-            const int grid = (int)std::min<long long>(ntiles, d->num_sms);
-            static long long* dbg2 = nullptr;   // HINT_B200_TC_DEBUG=1: cycle breakdown of CTA 0, printed after a sync
-            static const bool dbg_on = dev_getenv("HINT_B200_TC_DEBUG") != nullptr;
-            if (dbg_on) {
-                if (!dbg2) CUDA_TRY(cudaMalloc((void**)&dbg2, 16 * sizeof(long long)));
-                CUDA_TRY(cudaMemsetAsync(dbg2, 0, 16 * sizeof(long long), st));
-            }
-            long long* dp = dbg_on ? dbg2 : nullptr;
-            if (rev) { hint_tc2_kernel<true><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp); HINT_LAUNCHED(); }
-            else { hint_tc2_kernel<false><<<grid, kT2Threads, hp->tc2.smem_bytes, st>>>(hp->tc2.prog, x, c, packed, z, logdet, (long long)B, dp); HINT_LAUNCHED(); }
-            CUDA_TRY(cudaGetLastError());
-            if (dbg_on) {
-                long long h[16];
-                CUDA_TRY(cudaStreamSynchronize(st));
-                CUDA_TRY(cudaMemcpy(h, dbg2, sizeof(h), cudaMemcpyDeviceToHost));
-                const double nt = (double)std::max<long long>(1, h[6]);
-                std::fprintf(stderr, "[hint_b200 tc2 dbg] tiles/CTA %lld | issuer0 cyc/tile: wait_tile %.0f wait_prev_final %.0f wait_epi %.0f wait_chunk %.0f issue %.0f"
-                             " | epi warp0 cyc/tile: wait_x %.0f load %.0f wait_mma %.0f hidden %.0f wait_fin %.0f final %.0f store %.0f\n",
-                             h[6], h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt, h[14] / nt);
-            }
-            return HINT_OK;
-        }
-        return fail(HINT_ERR_UNSUPPORTED, "this block is outside the TF32 (tcgen05) kernel's envelope");
     }
     if ((rc = pack_weights(hp, *d, params, packed, st)) != HINT_OK) return rc;
     const Schedule& s = hp->p.fwd;
@@ -507,9 +443,8 @@ static int backward_impl(const hint_plan_t* hp_c, const float* z, const float* c
                          const float* dlogdet, float nll_scale, int64_t B, int32_t mode, float* x_rec, float* dx, float* dc, float* dparams,
                          void* workspace, size_t workspace_bytes, void* stream) {
     hint_plan* hp = const_cast<hint_plan*>(hp_c);
-    // HINT_MODE_TF32_TCGEN05 has no backward kernel of its own: it runs the FP32 CUDA-core sweep (which differentiates
-    // the exact function at the TF32-computed output).
-    int rc = check_common(hp, z, c, params, B, mode == HINT_MODE_TF32_TCGEN05 ? HINT_MODE_FP32 : mode);
+    if (mode == HINT_MODE_TF32_TCGEN05) mode = HINT_MODE_TF32_TC3;   // alias
+    int rc = check_common(hp, z, c, params, B, mode);
     if (rc != HINT_OK) return rc;
     if (!dparams) return fail(HINT_ERR_INVALID, "dparams is NULL");
     // HINT_MODE_TF32 backward: the register-chained kernel where the block fits its shape table, else the interpreter

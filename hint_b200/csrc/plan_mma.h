@@ -1,6 +1,6 @@
 // Schedule of the warp-MMA (mma.sync.m16n8k8 tf32) fused-tree kernels for one HINT block.
 //
-// Why a second tensor-core path next to the tcgen05 one (plan_tc.h): the coupling tree of hint.py:25-54 is made of
+// Why a second tensor-core path next to the tcgen05 one (plan_tc3.h): the coupling tree of hint.py:25-54 is made of
 // many SMALL dense layers (h = 67/33/16/8/8 for the d=43 model).  tcgen05.mma is issue-bound for N <= 64
 // (measured 38 cycles per MMA whatever N, profiles/ubench3_r01_mma_issue_tmem.txt) and its TMEM-resident tile
 // serialises the 15 dependent layer->epilogue round trips of one tile (profiles/tc2_cycle_breakdown_r01.txt),

@@ -39,16 +39,16 @@ extern "C" {
 #define HINT_MODE_TF32 1        /* tensor cores, operands rounded to 10-bit mantissa (warp-MMA fused-tree kernels;
                                    forward, inverse and backward)                                 */
 #define HINT_MODE_TF32X3 2      /* same kernels, 3xTF32 split (big*big + small*big + big*small): fp32-class accuracy */
-#define HINT_MODE_TF32_TCGEN05 3 /* tcgen05 kind::tf32 / TMEM forward+inverse kernel (backward runs the FP32 sweep)  */
+#define HINT_MODE_TF32_TCGEN05 3 /* alias of HINT_MODE_TF32_TC3 (one tcgen05 / TMEM kernel runs forward, inverse and backward)  */
 #define HINT_MODE_TF32_MMA 4    /* HINT_MODE_TF32 with the warp-MMA kernel forced for forward/inverse too (HINT_MODE_TF32
                                    itself picks the faster of the two forward kernels the block fits)                */
 
 #define HINT_MODE_TF32_CHAIN 5  /* HINT_MODE_TF32 with the register-chained warp-MMA kernels forced (HINT_MODE_TF32 picks
                                    them whenever the block fits their shape table)                                   */
 
-#define HINT_MODE_TF32_TC3 6    /* HINT_MODE_TF32 with the tcgen05 / TMEM training kernel forced for the backward (tensor-memory
-                                   accumulators, weight gradients as tcgen05.mma over shared-memory images); HINT_MODE_TF32 picks
-                                   it for the blocks the register-chained kernels do not cover                           */
+#define HINT_MODE_TF32_TC3 6    /* HINT_MODE_TF32 with the tcgen05 / TMEM kernel forced: forward / inverse transport programs and the
+                                   memory-free backward (tensor-memory accumulators, weight gradients as tcgen05.mma over shared-
+                                   memory images); HINT_MODE_TF32 picks it for the blocks the register-chained kernels do not cover */
 
 /* which workspace hint_workspace_bytes() sizes */
 #define HINT_WS_FORWARD 0

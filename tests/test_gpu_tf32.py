@@ -1,5 +1,5 @@
 """GPU parity tests of the tensor-core modes through the module / C ABI: "tf32" and "tf32x3" (warp-MMA fused-tree kernels:
-forward, inverse, backward) and "tf32_tcgen05" (tcgen05/TMEM forward + inverse kernel).
+forward, inverse, backward) and "tf32_tc3" / its alias "tf32_tcgen05" (the tcgen05 / TMEM kernel: transport programs + backward).
 
 Stated bound for single-pass TF32 (10-bit mantissa operands, fp32 accumulate, weights and hidden activations rounded to
 nearest, x columns truncated by the tensor core): max-norm error relative to max(1, max|ref|) of
