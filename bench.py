@@ -324,7 +324,7 @@ def run_ours(args, w, name):
         return out, (model, params, opt, trainer, x, c)
 
     B = args.batch or w["batch"]
-    tf32_peak = measure_tf32_peak(torch, dev) if rank == 0 else None
+    tf32_peak = measure_tf32_peak(torch, dev) if (rank == 0 and not args.skip_peak) else None
     hint_b200.set_precision(args.mode)
     model, params, opt, trainer, x, c = build(w, B, args.mode)
     timed_avg = make_timed_avg(B * w["d"] * 4 <= 126e6)
@@ -561,6 +561,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("HINT_B200_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3", "tf32_mma", "tf32_tcgen05", "tf32_chain", "tf32_tc3"])
     ap.add_argument("--cpu-sample", type=int, default=32768, help="samples per CPU step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-peak", action="store_true", help="do not measure the TF32 peak with cuBLAS in this run (profiler launch lists); "
+                                                             "the roofline then uses MEASURED_PEAKS.json's bf16 figures / 2")
     ap.add_argument("--quick", action="store_true", help="skip the extra modes and the sweep over the other BASELINE workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
