@@ -17,8 +17,9 @@ namespace {
 constexpr int kTmemCols = 512;
 constexpr int kHpMaxMulti = 128;   // hidden columns of a multi-node group (one M tile of the weight-gradient GEMMs)
 constexpr int kHpMaxSingle = 160;  // a single node may be wider (second M tile)
-constexpr int kHpMaxTransport = 232; // forward / inverse programs: 2 (h + 8) + operands <= 512 columns, MMA N <= 256
+constexpr int kHpMaxTransport = 400; // forward / inverse programs: the first hidden layer must fit TMEM next to a chunk of the second
 constexpr int kKaMax = 32, kOwMax = 32;
+constexpr int kKaMaxTransport = 64, kOwMaxTransport = 64;   // no images / accumulators keyed to them in the transport programs
 
 enum ResKind { R_TMEM = 0, R_IMG0 = 1 /* .. R_IMG0 + kT3Imgs - 1 */ };
 struct Res { int kind, lo, hi; };
@@ -70,13 +71,13 @@ struct Builder {
     // ---- weights ----
     // Appends the operand as K slabs (each an independent canonical block that fits one ring slot) and emits the
     // tcgen05.mma records that multiply the A segments with it into D.
-    void gemm_ts(const BOp& B, const std::vector<ASeg>& aseg, int d_col, bool commit) {
+    void gemm_ts(const BOp& B, const std::vector<ASeg>& aseg, int d_col, bool commit, bool zero_first = true) {
         const int max_kc = std::max(8, (t.slot_bytes / (B.N * 4)) / 8 * 8);
         // K steps in order: (a_col of each step)
         std::vector<int> acols;
         for (const ASeg& s : aseg) for (int i = 0; i < s.nk; ++i) acols.push_back(s.col + 8 * i);
         const int nk_total = B.K / 8;
-        bool first = true;
+        bool first = zero_first;
         for (int k0 = 0; k0 < nk_total;) {
             const int kc = std::min(max_kc / 8, nk_total - k0);      // K steps in this slab
             const int Kc = kc * 8;
@@ -197,8 +198,17 @@ static bool tmem_layout(T3Group& g, bool transport) {
     const int PW = g.HP + 8;
     int c = 0;
     if (transport) {
+        // first hidden layer whole (it is the K of the second), the second hidden layer whole when it fits, else (single wide
+        // node) in chunks of CH columns that the third layer consumes as K chunks: h2 never exists as a whole
+        const int rest = kTmemCols - PW - g.KA - g.OW - 8;
+        g.CH = 0;
+        if (rest < g.HP) {
+            if (g.nodes.size() != 1) return false;
+            g.CH = std::min(rest, 256) / 16 * 16;
+            if (g.CH < 32) return false;
+        }
         g.tm_p = c; c += PW;
-        g.tm_q = c; c += PW;
+        g.tm_q = c; c += (g.CH ? g.CH : g.HP) + 8;
         g.tm_ain = c; c += g.KA;
         g.tm_out = c; c += g.OW;
         g.tm_acc2 = g.tm_dout = g.tm_da = g.tm_acc1 = g.tm_acc3 = 0;
@@ -250,7 +260,8 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
                 trial.HP += hp; trial.KX += n.k; trial.OC += n.cout;
                 group_dims(trial, p.dc);
                 const bool fits = trial.nodes.size() == 1 ||
-                                  (trial.HP <= hp_cap && trial.KA <= kKaMax && trial.OW <= kOwMax && (int)trial.nodes.size() <= 16 && tmem_layout(trial, transport));
+                                  (trial.HP <= hp_cap && trial.KA <= (transport ? kKaMaxTransport : kKaMax) && trial.OW <= (transport ? kOwMaxTransport : kOwMax) &&
+                                   (int)trial.nodes.size() <= 16 && tmem_layout(trial, transport));
                 if (!fits) {
                     t.groups.push_back(g);
                     trial = T3Group();
@@ -265,7 +276,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         }
         for (T3Group& g : t.groups) {
             group_dims(g, p.dc);
-            if (g.KA > kKaMax || g.OW > kOwMax) { fail("a node's input/output width exceeds the tcgen05 training kernel's envelope"); return false; }
+            if (g.KA > (transport ? kKaMaxTransport : kKaMax) || g.OW > (transport ? kOwMaxTransport : kOwMax)) { fail("a node's input/output width exceeds the tcgen05 training kernel's envelope"); return false; }
             if (!tmem_layout(g, transport)) { fail("a tree level does not fit the 512 TMEM columns"); return false; }
         }
         return true;
@@ -286,13 +297,15 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
             t.sm_img[i] = o; t.img_rows[i] = i == 0 ? std::max(pad8(N2max), pad8(HPmax)) : pad8(HPmax);
             o += t.img_rows[i] * 512;
         }
-        t.sm_img[3] = o; t.img_rows[3] = pad8(N1max); o += t.img_rows[3] * 512;
-        t.sm_img[4] = o; t.img_rows[4] = pad8(OWmax); o += t.img_rows[4] * 512;
+        if (!transport) {     // the transport programs write no images at all (T3E_IN carries T3I_NOIMG)
+            t.sm_img[3] = o; t.img_rows[3] = pad8(N1max); o += t.img_rows[3] * 512;
+            t.sm_img[4] = o; t.img_rows[4] = pad8(OWmax); o += t.img_rows[4] * 512;
+        }
         t.sm_ring = o; o += nslots * slot;
         t.sm_tab16 = o; o += tab_bytes;
         t.sm_epis = o; o += epi_bytes;
         t.sm_xs = o; o += 128 * t.xp * 4;
-        t.sm_gs = o; o += 128 * t.xp * 4;
+        t.sm_gs = o; o += transport ? 0 : 128 * t.xp * 4;     // gradient state: backward only
         t.sm_os = o; o += 128 * t.op * 4;
         t.sm_stage = o; o += 0;
         t.sm_red = o; o += 4 * 32 * 4;
@@ -306,12 +319,15 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         return t.smem_bytes <= kSmemMax - 1024;   // 1 KB left for the kernel's static shared memory
     };
     bool placed = false;
-    for (int hp_cap : {128, 112, 96, 80, 64, 48, 32}) {
+    // backward: a multi-node group is one M tile of the weight-gradient GEMMs (128 hidden columns); the transport programs have no
+    // such limit, only the TMEM budget
+    const std::vector<int> caps = transport ? std::vector<int>{224, 192, 160, 128, 112, 96, 80, 64, 48, 32} : std::vector<int>{128, 112, 96, 80, 64, 48, 32};
+    for (int hp_cap : caps) {
         if (!build_groups(hp_cap)) return;   // `why` already set: no cap helps
         tab_bytes = 0; epi_bytes = 0;
         for (const T3Group& g : t.groups) {
             tab_bytes += 2 * (g.KA + g.OC + g.KX + p.dc + 1 + 6 * (int)g.nodes.size());
-            epi_bytes += (int)sizeof(T3Epi) * (16 + 6 * g.mtiles);   // steps of one group: 4 + 9 + 9 plus the flushes of the extra M tiles
+            epi_bytes += (int)sizeof(T3Epi) * (16 + 6 * g.mtiles + (g.CH ? 4 * ((g.HP + g.CH - 1) / g.CH) : 0));   // steps of one group: 4 + 9 + 9, flushes of extra M tiles, hidden chunks
         }
         tab_bytes = (tab_bytes + 15) & ~15;
         HPmax = N1max = N2max = OCmax = OWmax = 0; mtmax = 1;
@@ -321,7 +337,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         }
         t.op = OCmax | 1;
         if (transport) {
-            if (layout(0, 4, 16384) || layout(0, 3, 16384) || layout(0, 2, 16384) || layout(0, 2, 8192)) { placed = true; break; }
+            if (layout(0, 4, 32768) || layout(0, 3, 32768) || layout(0, 4, 16384) || layout(0, 3, 16384) || layout(0, 2, 16384) || layout(0, 2, 8192)) { placed = true; break; }
             continue;
         }
         if (layout(3, 3, 16384) || layout(2, 3, 16384) || layout(2, 2, 16384) || layout(2, 3, 8192) || layout(2, 2, 8192)) { placed = true; break; }
@@ -464,16 +480,28 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
 
         // ---- emitters ----
         auto e_in = [&]() {
-            T3Epi e{}; e.type = T3E_IN; e.a = tab_in; e.b = g.KA; e.c = g.tm_ain;
-            Acc a; a.wr.push_back({R_TMEM, g.tm_ain, g.tm_ain + g.KA}); a.wr.push_back({R_IMG0 + IMG_IN, 0, g.KA});
+            T3Epi e{}; e.type = T3E_IN; e.a = tab_in; e.b = g.KA; e.c = g.tm_ain; e.flags = transport ? T3I_NOIMG : 0;
+            Acc a; a.wr.push_back({R_TMEM, g.tm_ain, g.tm_ain + g.KA}); if (!transport) a.wr.push_back({R_IMG0 + IMG_IN, 0, g.KA});
             b.push_epi(e, a);
         };
-        auto e_hid = [&](int col0, int img, bool img_ones) {   // img < 0: no image
-            T3Epi e{}; e.type = T3E_HID; e.flags = (T3H_ONES | (img >= 0 ? T3H_IMG : 0) | (img >= 0 && img_ones ? T3H_IMG_ONES : 0));
-            e.a = col0; e.b = g.HP; e.c = (img < 0 ? 0 : img);
-            Acc a; a.rd.push_back({R_TMEM, col0, col0 + g.HP}); a.wr.push_back({R_TMEM, col0, col0 + g.HP + 8});
-            if (img >= 0) a.wr.push_back({R_IMG0 + img, 0, g.HP + (img_ones ? 8 : 0)});
+        auto e_hid = [&](int col0, int img, bool img_ones, int width = -1, bool ones = true) {   // img < 0: no image
+            const int w = width < 0 ? g.HP : width;
+            T3Epi e{}; e.type = T3E_HID; e.flags = ((ones ? T3H_ONES : 0) | (img >= 0 ? T3H_IMG : 0) | (img >= 0 && img_ones ? T3H_IMG_ONES : 0));
+            e.a = col0; e.b = w; e.c = (img < 0 ? 0 : img);
+            Acc a; a.rd.push_back({R_TMEM, col0, col0 + w}); a.wr.push_back({R_TMEM, col0, col0 + w + (ones ? 8 : 0)});
+            if (img >= 0) a.wr.push_back({R_IMG0 + img, 0, w + (img_ones ? 8 : 0)});
             b.push_epi(e, a);
+        };
+        // rows [n0, n1) / columns [k0, k1) of an operand
+        auto rows_of = [&](const BOp& B, int n0, int n1) {
+            BOp R; R.init(n1 - n0, B.K);
+            for (int n = n0; n < n1; ++n) for (int k = 0; k < B.K; ++k) R.at(n - n0, k) = B.src[(size_t)n * B.K + k];
+            return R;
+        };
+        auto cols_of = [&](const BOp& B, int k0, int k1) {
+            BOp R; R.init(B.N, k1 - k0);
+            for (int n = 0; n < B.N; ++n) for (int k = k0; k < k1; ++k) R.at(n, k - k0) = B.src[(size_t)n * B.K + k];
+            return R;
         };
         auto e_flush = [&](int net, int kind, int mt) {
             const int col0 = kind == T3F_W2 ? g.tm_acc2 : kind == T3F_W1 ? g.tm_acc1 : g.tm_acc3;
@@ -486,6 +514,29 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
             if (defer_flush && kind != T3F_W3) b.defer(e, a); else b.push_epi(e, a);   // the dW3 flush already runs behind the dH1 GEMM
         };
         auto fwd_chain = [&](int net, bool images, bool layer3) {
+            if (g.CH) {
+                // wide single node (transport programs only): layer 1 in N halves (MMA N <= 256); layer 2 in column chunks of CH
+                // whose relu'd result is the K chunk of a layer-3 partial product - h2 never exists as a whole
+                const auto& n = p.nodes[g.nodes[0]];
+                const BOp W1 = w1g(net), W2 = w2n(net, 0), W3 = w3g(net);
+                for (int n0 = 0; n0 < g.HP; n0 += 256) {
+                    const int n1 = std::min(g.HP, n0 + 256);
+                    b.gemm_ts(rows_of(W1, n0, n1), {{g.tm_ain, g.KA / 8}}, P + n0, n1 == g.HP);
+                }
+                e_hid(P, -1, false);
+                const int K2 = pad8(n.h);
+                for (int j0 = 0; j0 < g.HP; j0 += g.CH) {
+                    const int j1 = std::min(g.HP, j0 + g.CH), w = j1 - j0;
+                    const bool last = j1 == g.HP;
+                    b.gemm_ts(rows_of(W2, j0, j1), {{P, K2 / 8}, {P + g.HP, 1}}, Q, true);
+                    e_hid(Q, -1, false, w, last);
+                    BOp W3c = cols_of(W3, j0, last ? g.HP + 8 : j1);      // the last chunk carries the bias K step
+                    std::vector<ASeg> as{{Q, w / 8}};
+                    if (last) as.push_back({Q + w, 1});
+                    b.gemm_ts(W3c, as, g.tm_out, last, j0 == 0);
+                }
+                return;
+            }
             b.gemm_ts(w1g(net), {{g.tm_ain, g.KA / 8}}, P, true);
             e_hid(P, images ? IMG_H1 : -1, true);
             for (int q = 0; q < nn; ++q) {

@@ -74,6 +74,8 @@ struct T3Epi {
     int32_t off;         // partial-buffer offset (T3E_FLUSH, T3E_CPL, T3E_DS)
     int32_t a, b, c, d, e, f, g, h;   // per type, see plan_tc3.cpp: the emitters in build_tc3_plan()
 };
+// T3E_IN flags
+enum : int32_t { T3I_NOIMG = 1 };   // transport programs: no input image
 // T3E_HID flags
 enum : int32_t { T3H_IMG = 1, T3H_ONES = 2, T3H_IMG_ONES = 4 };
 // T3E_DHID flags
@@ -102,6 +104,7 @@ struct T3Group {
     int N2 = 0;      // N of the dW2 GEMM: pad16(HP + 8)
     int N1 = 0;      // N of the dW1 / dA GEMMs: pad16(KX + dc + 1)
     int mtiles = 1;  // M tiles of the weight-gradient GEMMs
+    int CH = 0;      // transport programs, wide single node: the second hidden layer is produced and consumed in chunks of CH columns
     int part[2][4];  // partial-buffer offsets per net: dW2 block, dW1 block, dW3 block, db3 vector
     // TMEM map of this group (columns)
     int tm_p = 0, tm_q = 0, tm_acc2 = 0, tm_ain = 0, tm_dout = 0, tm_out = 0, tm_da = 0, tm_acc1 = 0, tm_acc3 = 0;

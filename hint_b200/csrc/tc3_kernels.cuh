@@ -238,7 +238,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                     for (int i = tid; i < 128 * dc; i += 32 * kT3EpiWarps) {
                         const int s = i / dc, j = i - s * dc;
                         xs_all[s * P.xp + d + j] = i < nc ? __ldg(gc + i) : 0.f;
-                        gs_all[s * P.xp + d + j] = 0.f;
+                        if (P.kind == T3K_BACKWARD) gs_all[s * P.xp + d + j] = 0.f;   // the transport programs have no gradient state
                     }
                 }
             }
@@ -266,13 +266,14 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                     case T3E_IN: {
                         if (wg == 0) {
                             unsigned char* im3 = img_ptr(3);
+                            const bool to_img = !(e.flags & T3I_NOIMG);
                             for (int c0 = 0; c0 < e.b; c0 += 8) {
                                 float v[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
                                     const int code = s_tab[e.a + c0 + j];
                                     v[j] = t3_round(code >= 0 ? XS[code] : (code == -2 ? 1.f : 0.f));
-                                    *reinterpret_cast<float*>(im3 + (uint32_t)(c0 >> 3) * 1024u + xo[j]) = v[j];
+                                    if (to_img) *reinterpret_cast<float*>(im3 + (uint32_t)(c0 >> 3) * 1024u + xo[j]) = v[j];
                                 }
                                 st8(lane_base + (uint32_t)(e.c + c0), v);
                             }

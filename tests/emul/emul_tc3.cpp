@@ -144,7 +144,7 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                         for (int col = 0; col < e.b; ++col) {
                             const int code = tb[e.a + col];
                             const float v = rt(code >= 0 ? XS[(size_t)s * xp + code] : (code == -2 ? 1.f : 0.f));
-                            tm(s, e.c + col) = v; im(3, col, s) = v;
+                            tm(s, e.c + col) = v; if (!(e.flags & T3I_NOIMG)) im(3, col, s) = v;
                         }
                     break;
                 case T3E_HID:
