@@ -284,7 +284,7 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
 
     // ---- shared memory map ----
     t.xp = (p.d + p.dc) | 1;
-    int HPmax = 0, N1max = 0, N2max = 0, OCmax = 0, OWmax = 0, mtmax = 1, tab_bytes = 0, epi_bytes = 0;
+    int HPmax = 0, N1max = 0, N2max = 0, OCmax = 0, OWmax = 0, KAmax = 0, KDmax = 0, mtmax = 1, tab_bytes = 0, epi_bytes = 0;
     auto layout = [&](int nimg, int nslots, int slot) {
         int o = 0;
         t.sm_bars = o; o += 1024;
@@ -293,13 +293,19 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         // An M tile reads 128 rows from its first row group: rows past an image land in the regions that follow it
         // (finite or not, they only reach accumulator rows that are never flushed) - the tail check below keeps
         // those reads inside the CTA's allocation.
+        // Rows are allocated for what the epilogue WRITES (hidden features + the ones block, inputs, outputs), not for the MMA's
+        // N (a multiple of 16): as a B operand an image is read for N rows from its first row, and the rows past the allocation
+        // land in the regions that follow it - garbage that only reaches accumulator columns no parameter maps to.  The shared
+        // memory saved this way pays for 32 KB weight slabs: the single issuer thread spends ~450 cycles of its own per record
+        // (barrier poll, descriptor arithmetic, two commits) against 65 cycles of tensor time per MMA, so a record must carry
+        // 8 MMAs, not 4, to keep the pipe busy.
         for (int i = 0; i < nimg; ++i) {
-            t.sm_img[i] = o; t.img_rows[i] = i == 0 ? std::max(pad8(N2max), pad8(HPmax)) : pad8(HPmax);
+            t.sm_img[i] = o; t.img_rows[i] = i == 0 ? pad8(HPmax + 8) : pad8(HPmax);
             o += t.img_rows[i] * 512;
         }
         if (!transport) {     // the transport programs write no images at all (T3E_IN carries T3I_NOIMG)
-            t.sm_img[3] = o; t.img_rows[3] = pad8(N1max); o += t.img_rows[3] * 512;
-            t.sm_img[4] = o; t.img_rows[4] = pad8(OWmax); o += t.img_rows[4] * 512;
+            t.sm_img[3] = o; t.img_rows[3] = pad8(KAmax); o += t.img_rows[3] * 512;
+            t.sm_img[4] = o; t.img_rows[4] = pad8(KDmax); o += t.img_rows[4] * 512;
         }
         t.sm_ring = o; o += nslots * slot;
         t.sm_tab16 = o; o += tab_bytes;
@@ -309,10 +315,15 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
         t.sm_os = o; o += 128 * t.op * 4;
         t.sm_stage = o; o += 0;
         t.sm_red = o; o += 4 * 32 * 4;
-        // tail: the furthest byte an over-reading M tile can touch
+        // tail: the furthest byte an over-reading M tile (A operand, 128 rows per tile) or B operand (N rows) can touch
         for (int i = 0; i < nimg; ++i) {
             const int last = t.sm_img[i] + 3 * t.img_rows[i] * 128 + (mtmax * 128) * 128;
             o = std::max(o, last);
+        }
+        if (!transport) {
+            o = std::max(o, t.sm_img[0] + 3 * t.img_rows[0] * 128 + N2max * 128);
+            o = std::max(o, t.sm_img[3] + 3 * t.img_rows[3] * 128 + N1max * 128);
+            o = std::max(o, t.sm_img[4] + 3 * t.img_rows[4] * 128 + OWmax * 128);
         }
         t.n_imgs_hidden = nimg; t.n_slots = nslots; t.slot_bytes = slot;
         t.smem_bytes = (o + 15) & ~15;
@@ -330,17 +341,18 @@ void build_tc3_plan(const Plan& p, T3Plan& t, int kind) {
             epi_bytes += (int)sizeof(T3Epi) * (16 + 6 * g.mtiles + (g.CH ? 4 * ((g.HP + g.CH - 1) / g.CH) : 0));   // steps of one group: 4 + 9 + 9, flushes of extra M tiles, hidden chunks
         }
         tab_bytes = (tab_bytes + 15) & ~15;
-        HPmax = N1max = N2max = OCmax = OWmax = 0; mtmax = 1;
+        HPmax = N1max = N2max = OCmax = OWmax = KAmax = KDmax = 0; mtmax = 1;
         for (const T3Group& g : t.groups) {
+            KAmax = std::max(KAmax, g.KA); KDmax = std::max(KDmax, g.KD);
             HPmax = std::max(HPmax, g.HP); N1max = std::max(N1max, g.N1); N2max = std::max(N2max, g.N2);
             OCmax = std::max(OCmax, g.OC); OWmax = std::max(OWmax, g.OW); mtmax = std::max(mtmax, g.mtiles);
         }
         t.op = OCmax | 1;
         if (transport) {
-            if (layout(0, 4, 32768) || layout(0, 3, 32768) || layout(0, 4, 16384) || layout(0, 3, 16384) || layout(0, 2, 16384) || layout(0, 2, 8192)) { placed = true; break; }
+            if (layout(0, 4, 36864) || layout(0, 3, 36864) || layout(0, 4, 32768) || layout(0, 3, 32768) || layout(0, 4, 16384) || layout(0, 3, 16384) || layout(0, 2, 16384) || layout(0, 2, 8192)) { placed = true; break; }
             continue;
         }
-        if (layout(3, 3, 16384) || layout(2, 3, 16384) || layout(2, 2, 16384) || layout(2, 3, 8192) || layout(2, 2, 8192)) { placed = true; break; }
+        if (layout(2, 2, 36864) || layout(2, 2, 32768) || layout(3, 3, 16384) || layout(2, 3, 16384) || layout(2, 2, 16384) || layout(2, 3, 8192) || layout(2, 2, 8192)) { placed = true; break; }
     }
     if (!placed) return fail("the block's widest level does not fit shared memory");
 

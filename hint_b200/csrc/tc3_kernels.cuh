@@ -120,8 +120,12 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
             uint32_t slot = 0, ph = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int ch = 0; ch < P.n_chunks; ++ch) {
+                    // descriptor from the read-only path: the table is re-read for every tile and stays in L1.  A plain global
+                    // load here cost an exposed L2 round trip per chunk and capped the ring at one chunk per ~600 cycles
+                    // whatever its depth (every record of a hidden-layer GEMM waited for its slab).
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.chunks) + ch);
+                    T3Chunk ck; ck.g_off = raw.x; ck.bytes = raw.y;
                     mbar_wait(bars + T3B_EMPTY + slot, ph ^ 1);
-                    const T3Chunk ck = P.chunks[ch];
                     mbar_arrive_expect_tx(bars + T3B_FULL + slot, ck.bytes);
                     bulk_g2s(ring + (size_t)slot * P.slot_bytes, W + ck.g_off, ck.bytes, bars + T3B_FULL + slot);
                     if (++slot == (uint32_t)P.n_slots) { slot = 0; ph ^= 1; }
@@ -141,8 +145,17 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
                 int waited = -1;
                 const bool pt = blockIdx.x == 0 && tile_iter == 1;   // developer timeline of CTA 0's second tile
+                // The records live in the kernel-parameter (constant) bank, which keeps every MMA operand uniform, but a tile walks
+                // more records than the constant cache holds: fetching a record right before its use exposed a cache miss per
+                // record (~350 cycles, the tensor pipe idling behind every 4-MMA record).  The NEXT record is therefore fetched while
+                // the current one is being issued.
+                uint32_t n0 = P.mmas[0].w[0], n1 = P.mmas[0].w[1], n2 = P.mmas[0].w[2], n3 = P.mmas[0].w[3], n4 = P.mmas[0].w[4];
                 for (int i = 0; i < P.n_mma; ++i) {
-                    const uint32_t w0 = P.mmas[i].w[0], w1 = P.mmas[i].w[1], w2 = P.mmas[i].w[2], w3 = P.mmas[i].w[3], w4 = P.mmas[i].w[4];
+                    const uint32_t w0 = n0, w1 = n1, w2 = n2, w3 = n3, w4 = n4;
+                    {
+                        const int nx = i + 1 < P.n_mma ? i + 1 : 0;
+                        n0 = P.mmas[nx].w[0]; n1 = P.mmas[nx].w[1]; n2 = P.mmas[nx].w[2]; n3 = P.mmas[nx].w[3]; n4 = P.mmas[nx].w[4];
+                    }
                     const uint32_t m_idesc = w0, m_boff = w1, m_dcol = w2 & 0xFFFFu, m_acol = w2 >> 16, m_nk = w3 & 0xFFFFu, m_sbo16 = w3 >> 16;
                     const uint32_t m_flags = w4 & 0xFFFFu;
                     const int m_wait = (int)w4 >> 16;   // arithmetic shift: sign-extended 16-bit field
@@ -153,6 +166,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                         waited = m_wait;
                     }
                     if (prof && pt && i < 1024) prof[i] = clock64();
+                    long long t_full = 0, t_mma = 0;
                     uint32_t acc = (m_flags & T3M_ZERO) ? 0u : 1u;
                     if (!(m_flags & T3M_SS)) {
                         if (m_flags & T3M_NEWCHUNK) {
@@ -160,6 +174,7 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                             mbar_wait(bars + T3B_FULL + cur, nph);
                             if (++nslot == (uint32_t)P.n_slots) { nslot = 0; nph ^= 1; }
                         }
+                        if (prof && pt) t_full = clock64();
                         uint32_t b_lo = ((ring16 + cur * slot16 + (m_boff >> 4)) & 0x3FFFu) | (8u << 16);   // LBO = 128 B
                         const uint32_t b_hi = m_sbo16 | (1u << 14);                                            // SBO, descriptor version 1
                         uint32_t a_t = m_acol;
@@ -182,7 +197,9 @@ hint_tc3_bwd_kernel(const __grid_constant__ T3Prog P, const float* __restrict__ 
                             acc = 1u;
                         }
                     }
+                    if (prof && pt) t_mma = clock64();
                     if (m_flags & T3M_COMMIT) { commit(bars + T3B_MMA + (msig % kT3NB)); ++msig; }
+                    if (prof && pt && i < 512) { prof[4096 + 3 * i] = t_full; prof[4097 + 3 * i] = t_mma; prof[4098 + 3 * i] = clock64(); }
                 }
                 ebase += (uint32_t)P.n_epi;
                 if (dbg) commit(bars + T3B_DONE);   // developer dump (tests/cuda/dbg_tc3.py): everything issued has completed

@@ -22,7 +22,7 @@ def main():
     lib = _lib.load()
     nbytes = lib.hint_workspace_bytes(tp._h, B, _lib.WS_BACKWARD)
     ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    prof = torch.zeros(4096, dtype=torch.int64, device=dev)
+    prof = torch.zeros(8192, dtype=torch.int64, device=dev)
     dx = torch.zeros(B, d, device=dev); dflat = torch.zeros_like(flat)
     info = (ctypes.c_int32 * 4096)()
     vp = ctypes.c_void_p
@@ -55,7 +55,7 @@ def main():
     ss = np.array([(info[1024 + i] >> 8) & 1 for i in range(nm)])
     nk = np.array([info[1024 + i] & 0xFF for i in range(nm)])
     if verbose:
-        for i in range(nm): print(f"  rec {i:3d} {'SS' if ss[i] else 'TS'} N={info[1024 + i] >> 16:3d} nk={nk[i]:2d} flags={(info[1024 + i] >> 8) & 0xFF:02x} issued t={iss[i] - t0:7d}  (+{0 if i == 0 else gaps[i - 1]})")
+        for i in range(nm): print(f"  rec {i:3d} {'SS' if ss[i] else 'TS'} N={info[1024 + i] >> 16:3d} nk={nk[i]:2d} flags={(info[1024 + i] >> 8) & 0xFF:02x} issued t={iss[i] - t0:7d}  (+{0 if i == 0 else gaps[i - 1]})  fetch+waits {p[4096 + 3 * i] - iss[i] if i < 512 else -1:5d}  mma issue {p[4097 + 3 * i] - p[4096 + 3 * i] if i < 512 else -1:5d}  commit {p[4098 + 3 * i] - p[4097 + 3 * i] if i < 512 else -1:5d}")
     print(f"  issuer: first record t={iss[0] - t0}, last t={iss[-1] - t0}; median gap per record {int(np.median(gaps))}; records with gap > 1000: {(gaps > 1000).sum()} (sum {gaps[gaps > 1000].sum()})")
 
 if __name__ == "__main__":

@@ -93,6 +93,7 @@ static int run_tc3(int d, int dc, const int* c_internal, int n_internal, double 
                 const int r = m.a_col * 8 + j;
                 if (r >= t.img_rows[ai]) { for (int n = 0; n < N; ++n) acc[(size_t)j * N + n] = NAN; continue; }   // over-read rows: never flushed
                 for (int n = 0; n < N; ++n) {
+                    if (n >= t.img_rows[bi]) { acc[(size_t)j * N + n] = NAN; continue; }   // B rows past the allocation: columns no parameter maps to
                     double a = 0;
                     for (int s = 0; s < 128; ++s) a += (double)opnd(im(ai, r, s)) * (double)opnd(im(bi, n, s));
                     acc[(size_t)j * N + n] = a;
