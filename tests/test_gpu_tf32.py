@@ -302,7 +302,8 @@ def test_briefly_trained_weights_meet_the_stated_tf32_bound(cfg):
     0.005*randn; 300 steps on a fixed batch of 2048 standardised GMM samples: max|w| reaches 1.3 .. 2.5) in the FP32 mode on the
     GPU, then checks every block in the benchmarked mode `tf32` against the fp64 oracle on the activations the flow actually sees.
 
-    Stated bound of the single-pass TF32 mode on trained weights, relative to max(1, |ref|_inf):
+    Stated bound of the single-pass TF32 mode on trained weights: BASELINE.md section 5's own metric, the relative (L2) error of
+    z, <= 2e-3; and in the stricter max-norm metric of these tests, relative to max(1, |ref|_inf):
         z <= 5e-3 (measured 3e-4 .. 4.6e-3), log-det <= 1e-3 (measured 8e-5 .. 9.7e-4), x-reconstruction <= 1e-4,
         gradients (relative L2) dx <= 3e-2, dparams <= 1e-2 (measured 3.6e-3 .. 2.2e-2 / 9e-4 .. 8e-3).
     BASELINE.md section 5 suggested z <= 2e-3 from an emulation on weights with max|w| <= 1.3; this fixture trains harder and the
@@ -355,12 +356,14 @@ def test_briefly_trained_weights_meet_the_stated_tf32_bound(cfg):
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = old_tf32
         ez, eJ, ex = _err(z, z_ref.numpy()), _err(J, J_ref.numpy()), _err(xr, h.double().cpu().numpy())
+        rz = _l2(z, z_ref.numpy())       # BASELINE.md section 5's own metric: relative (L2) error of z
         gdx, gdp = _l2(dx, dx_ref.numpy()), _l2(dflat, dp_ref.numpy())
         tz, tJ = _err(zt, z_ref.numpy()), _err(Jt, J_ref.numpy())
         tdx, tdp = _l2(dxt, dx_ref.numpy()), _l2(dpt, dp_ref.numpy())
-        _report(f"trained {name:18s} block {bi} max|w| {float(flat.abs().max()):.2f}", z=ez, J=eJ, xrec=ex, dx=gdx, dparams=gdp,
+        _report(f"trained {name:18s} block {bi} max|w| {float(flat.abs().max()):.2f}", z=ez, z_relL2=rz, J=eJ, xrec=ex, dx=gdx, dparams=gdp,
                 torch_tf32_z=tz, torch_tf32_J=tJ, torch_tf32_dx=tdx, torch_tf32_dparams=tdp)
         assert ez <= 5e-3 and eJ <= 1e-3
+        assert rz <= 2e-3                # "single-pass TF32 <= 2e-3 relative on z" in its relative-error metric
         assert ex <= 1e-4 * max(1.0, float(z_ref.abs().max()))
         assert gdx <= 3e-2 and gdp <= 1e-2
         assert ez <= 1.5 * tz + 2e-4 and eJ <= 1.5 * tJ + 2e-4
