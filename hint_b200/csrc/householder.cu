@@ -8,8 +8,8 @@
 //                          walked backwards by W_{k-1} = W_k H_k while dW is pulled back by G_{k-1} = G_k H_k; per reflection
 //                          only matrix-vector products (a = G v, b = W'^T a, c = W' v, e = G^T c):
 //                              dv = -2/s (b + e) + 4 (c . a) / s^2 v,   s = |v|^2,  W' = W_{k-1}
-//   hh_apply_kernel        y = x W or x W^T: FP32 FFMA (the mixing must stay orthogonal to 1e-6: no TF32), W resident in shared
-//                          memory per CTA, 4 x 4 register tiles, 128-row tiles; HBM-bound for d <= 43, FFMA-bound at d = 100
+//   hh_apply_kernel        y = x W or x W^T: error-compensated 3 x TF32 warp MMAs (fp32-grade: the mixing must stay orthogonal to
+//                          1e-6), W resident in shared memory, per-warp cp.async double-buffered row ranges
 //   hh_wgrad_kernel        dW = x^T dz: per-CTA partials in registers over its row tiles, fixed-order second stage (deterministic)
 #include <cuda_runtime.h>
 
@@ -113,54 +113,121 @@ __global__ void __launch_bounds__(kHhThreads) hh_matrix_bwd_kernel(const float* 
     }
 }
 
-// y[r, :] = x[r, :] W (or W^T).  CTA = 128 rows; thread (rg = tid / 8, cg = tid % 8) owns rows 4 rg .. 4 rg + 3 and the column
-// quads cg, cg + 8, ...  Shared memory: W [d][dq4] (dq4 = d rounded up to 4, zero padded), x tile [128][d + 1].
-constexpr int kHhRows = 128;
+// y[r, :] = x[r, :] W (or W^T) on the tensor cores with fp32-grade accuracy: both operands are split into tf32 hi + lo parts
+// and every product is three `mma.m16n8k8.tf32` (lo*hi, hi*lo, hi*hi; the dropped lo*lo term is 2^-22 relative), fp32
+// accumulation.  (An FFMA version of this kernel was bound by shared-memory wavefronts at 15 TFLOP/s: a 4 x 4 register tile needs
+// one wavefront per two FFMA instructions, `profiles/ncu_r02_hh_apply.txt`.)  Warps are independent: a warp owns RW = 16 MT
+// consecutive rows = one CONTIGUOUS range of x, fetched by 16-byte cp.async into its private double buffer (same layout as in
+// global memory) while it multiplies the previous range; the products are staged in the consumed buffer and leave as 128-bit
+// stores; no CTA barrier in the loop.  W is resident in shared memory, already split (hi and lo images, zero padded to [K8][NP],
+// NP mod 16 = 8: B fragments conflict-free).
+__device__ __forceinline__ void hh_cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hh_cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t hh_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void hh_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = hh_tf32(v);
+    lo = hh_tf32(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void hh_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// a contiguous range of n floats global -> shared (16-byte copies when the global side is aligned)
+__device__ __forceinline__ void hh_range_fetch(float* dst, const float* src, int n, bool vec, int lane) {
+    const int n4 = vec ? n >> 2 : 0;
+    for (int i = lane; i < n4; i += 32) hh_cp_async16(dst + 4 * i, src + 4 * i);
+    for (int i = 4 * n4 + lane; i < n; i += 32) hh_cp_async4(dst + i, src + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
-__global__ void __launch_bounds__(kHhThreads) hh_apply_kernel(const float* __restrict__ x, const float* __restrict__ W, long long B, int d,
-                                                              int transpose, float* __restrict__ y) {
+constexpr int kHhApplyThreads = 512;
+
+// MT m-tiles of 16 rows per warp, all NT <= NTC output n-tiles accumulated in one pass over K: (MT, NTC) = (2, 6) for d <= 48,
+// (1, 16) for d <= 128.
+template <int MT, int NTC>
+__global__ void __launch_bounds__(kHhApplyThreads) hh_apply_kernel(const float* __restrict__ x, const float* __restrict__ W, long long B, int d,
+                                                                   int transpose, float* __restrict__ y) {
     extern __shared__ __align__(16) float sm[];
-    const int d4 = (d + 3) & ~3, xp = d + 1;
-    float* Ws = sm;                    // [d][d4]
-    float* Xs = Ws + d * d4;           // [128][xp]
-    for (int i = threadIdx.x; i < d * d4; i += kHhThreads) {
-        const int k = i / d4, j = i - k * d4;
-        Ws[i] = j < d ? (transpose ? W[(size_t)j * d + k] : W[(size_t)k * d + j]) : 0.f;
+    constexpr int RW = 16 * MT;
+    const int K8 = (d + 7) & ~7, NT = K8 >> 3, NP = K8 + ((K8 & 15) == 8 ? 0 : 8), bufsz = (RW * d + 8 + 3) & ~3;
+    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t* Wh = reinterpret_cast<uint32_t*>(sm);    // [K8][NP] tf32 hi parts, then [K8][NP] lo parts
+    uint32_t* Wl = Wh + K8 * NP;
+    float* Xw = sm + 2 * K8 * NP + warp * (2 * bufsz); // this warp's two row ranges, rows of pitch d (as in global memory) + 8 floats of slack
+    for (int i = threadIdx.x; i < K8 * NP; i += blockDim.x) {
+        const int k = i / NP, j = i - k * NP;
+        hh_split((j < d && k < d) ? (transpose ? W[(size_t)j * d + k] : W[(size_t)k * d + j]) : 0.f, Wh[i], Wl[i]);
     }
-    const int rg = threadIdx.x >> 3, cg = threadIdx.x & 7;
-    const long long ntiles = (B + kHhRows - 1) / kHhRows;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * kHhRows;
-        const int rows = (int)((B - row0) < kHhRows ? (B - row0) : kHhRows);
-        __syncthreads();
-        const float* gx = x + row0 * d;
-        for (int i = threadIdx.x; i < kHhRows * d; i += kHhThreads) {
-            const int r = i / d, k = i - r * d;
-            Xs[r * xp + k] = r < rows ? __ldg(gx + i) : 0.f;
-        }
-        __syncthreads();
-        for (int q = cg; q * 4 < d; q += 8) {
-            float acc[4][4] = {};
-            const float* xr = Xs + (4 * rg) * xp;
-            for (int k = 0; k < d; ++k) {
-                const float4 w = *reinterpret_cast<const float4*>(Ws + k * d4 + 4 * q);
-                const float x0 = xr[k], x1 = xr[xp + k], x2 = xr[2 * xp + k], x3 = xr[3 * xp + k];
-                acc[0][0] = fmaf(x0, w.x, acc[0][0]); acc[0][1] = fmaf(x0, w.y, acc[0][1]); acc[0][2] = fmaf(x0, w.z, acc[0][2]); acc[0][3] = fmaf(x0, w.w, acc[0][3]);
-                acc[1][0] = fmaf(x1, w.x, acc[1][0]); acc[1][1] = fmaf(x1, w.y, acc[1][1]); acc[1][2] = fmaf(x1, w.z, acc[1][2]); acc[1][3] = fmaf(x1, w.w, acc[1][3]);
-                acc[2][0] = fmaf(x2, w.x, acc[2][0]); acc[2][1] = fmaf(x2, w.y, acc[2][1]); acc[2][2] = fmaf(x2, w.z, acc[2][2]); acc[2][3] = fmaf(x2, w.w, acc[2][3]);
-                acc[3][0] = fmaf(x3, w.x, acc[3][0]); acc[3][1] = fmaf(x3, w.y, acc[3][1]); acc[3][2] = fmaf(x3, w.z, acc[3][2]); acc[3][3] = fmaf(x3, w.w, acc[3][3]);
-            }
+    __syncthreads();
+    const bool vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0, vec_out = (reinterpret_cast<uintptr_t>(y) & 15) == 0;   // range offsets are multiples of 64 bytes
+    const long long nranges = (B + RW - 1) / RW, stride = (long long)gridDim.x * nw;
+    auto floats_of = [&](long long r) { const long long left = B - r * RW; return (int)(left < RW ? left : RW) * d; };
+    long long rng = (long long)blockIdx.x * nw + warp;
+    if (rng < nranges) hh_range_fetch(Xw, x + rng * RW * d, floats_of(rng), vec_in, lane);
+    int buf = 0;
+    for (; rng < nranges; rng += stride, buf ^= 1) {
+        float* Xb = Xw + buf * bufsz;
+        const int n = floats_of(rng);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (rng + stride < nranges) hh_range_fetch(Xw + (buf ^ 1) * bufsz, x + (rng + stride) * RW * d, floats_of(rng + stride), vec_in, lane);
+        float acc[MT][NTC][4] = {};
+        for (int ks = 0; ks < NT; ++ks) {
+            uint32_t ah[MT][4], al[MT][4];
+            const bool k0 = 8 * ks + t < d, k1 = 8 * ks + t + 4 < d;   // columns beyond d hold the next row: mask them (last k-step only)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = 4 * rg + i;
-                if (r >= rows) continue;
-                float* gy = y + (row0 + r) * d + 4 * q;
+            for (int i = 0; i < MT; ++i) {
+                const float* ap = Xb + (16 * i + g) * d + 8 * ks + t;
+                hh_split(k0 ? ap[0] : 0.f, ah[i][0], al[i][0]);
+                hh_split(k0 ? ap[8 * d] : 0.f, ah[i][1], al[i][1]);
+                hh_split(k1 ? ap[4] : 0.f, ah[i][2], al[i][2]);
+                hh_split(k1 ? ap[8 * d + 4] : 0.f, ah[i][3], al[i][3]);
+            }
+            const uint32_t* bh = Wh + (8 * ks + t) * NP + g;
+            const uint32_t* bl = Wl + (8 * ks + t) * NP + g;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (4 * q + j < d) gy[j] = acc[i][j];
+            for (int j = 0; j < NTC; ++j) {
+                if (j < NT) {
+                    const uint32_t bh0 = bh[8 * j], bh1 = bh[8 * j + 4 * NP], bl0 = bl[8 * j], bl1 = bl[8 * j + 4 * NP];
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        hh_mma(acc[i][j], al[i], bh0, bh1);
+                        hh_mma(acc[i][j], ah[i], bl0, bl1);
+                        hh_mma(acc[i][j], ah[i], bh0, bh1);
+                    }
+                }
             }
         }
+        __syncwarp();                                  // every lane is done reading the range: stage the products in its place
+#pragma unroll
+        for (int j = 0; j < NTC; ++j) {
+            const int col = 8 * j + 2 * t;
+            if (j < NT && col < d) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    float* r0 = Xb + (16 * i + g) * d + col;
+                    float* r1 = r0 + 8 * d;
+                    r0[0] = acc[i][j][0]; r1[0] = acc[i][j][2];
+                    if (col + 1 < d) { r0[1] = acc[i][j][1]; r1[1] = acc[i][j][3]; }
+                }
+            }
+        }
+        __syncwarp();
+        float* gy = y + rng * RW * d;
+        const int n4 = vec_out ? n >> 2 : 0;
+        for (int i = lane; i < n4; i += 32) __stcs(reinterpret_cast<float4*>(gy) + i, *reinterpret_cast<const float4*>(Xb + 4 * i));
+        for (int i = 4 * n4 + lane; i < n; i += 32) __stcs(gy + i, Xb[i]);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // partial[cta][i][j] = sum over the CTA's rows of x[r][i] dz[r][j];  thread (ig = tid / 16, jg = tid % 16) owns the 4 x 4 blocks
@@ -255,18 +322,31 @@ cudaError_t hh_matrix_backward(const float* Vs, const float* W, const float* dW,
     return cudaGetLastError();
 }
 
+namespace {
+template <int MT, int NTC>
+cudaError_t hh_apply_launch(const float* x, const float* W, long long B, int d, int transpose, float* y, cudaStream_t st) {
+    const int K8 = (d + 7) & ~7, NP = K8 + ((K8 & 15) == 8 ? 0 : 8), RW = 16 * MT, bufsz = (RW * d + 8 + 3) & ~3;
+    const size_t wbytes = sizeof(float) * 2 * (size_t)K8 * NP, per_warp = sizeof(float) * 2 * (size_t)bufsz;
+    int nw = (int)(((size_t)216 * 1024 - wbytes) / per_warp);
+    nw = nw > kHhApplyThreads / 32 ? kHhApplyThreads / 32 : nw < 1 ? 1 : nw;
+    const size_t smem = wbytes + nw * per_warp;
+    const void* fn = (const void*)hh_apply_kernel<MT, NTC>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * nw, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const long long nranges = (B + RW - 1) / RW, want = (nranges + nw - 1) / nw, cap = (long long)hh_sms() * per_sm;
+    hh_apply_kernel<MT, NTC><<<(int)(want < cap ? want : cap), 32 * nw, smem, st>>>(x, W, B, d, transpose, y); HINT_LAUNCHED();
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t hh_apply(const float* x, const float* W, long long B, int d, int transpose, float* y, cudaStream_t st) {
     if (d < 1 || d > kHhMaxD || B < 0) return cudaErrorInvalidValue;
     if (B == 0) return cudaSuccess;
-    const int d4 = (d + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)d * d4 + (size_t)kHhRows * (d + 1));
-    cudaError_t e = cudaFuncSetAttribute((const void*)hh_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const long long ntiles = (B + kHhRows - 1) / kHhRows;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    const int grid = (int)(ntiles < (long long)hh_sms() * per_sm ? ntiles : (long long)hh_sms() * per_sm);
-    hh_apply_kernel<<<grid, kHhThreads, smem, st>>>(x, W, B, d, transpose, y); HINT_LAUNCHED();
-    return cudaGetLastError();
+    return d <= 48 ? hh_apply_launch<2, 6>(x, W, B, d, transpose, y, st) : hh_apply_launch<1, 16>(x, W, B, d, transpose, y, st);
 }
 
 size_t hh_wgrad_workspace_bytes(int d) { return sizeof(float) * (size_t)hh_sms() * 2 * d * d; }

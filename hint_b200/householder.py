@@ -1,6 +1,6 @@
 """Host side of the inter-block Householder mixing (FrEIA ``HouseholderPerm`` as the reference's configs use it,
 e.g. configs/plus_shape/unconditional_hint_4_3.py:60-71).  Thin autograd wrapper over the C ABI (include/hint_b200.h:
-hint_householder_*): W is rebuilt from the reflections by one kernel per call when they are trainable, applied by an FP32 FFMA
+hint_householder_*): W is rebuilt from the reflections by one kernel per call when they are trainable, applied by an error-compensated 3 x TF32 tensor-core
 kernel, and differentiated without stored intermediates.  CUDA tensors only - there is no CPU path."""
 import torch
 import torch.nn as nn
@@ -30,10 +30,10 @@ def householder_matrix(Vs):
 
 
 def householder_apply(x, W, transpose=False):
-    """y = x W (or x W^T), FP32."""
+    """y = x W (or x W^T), fp32-grade (error-compensated 3 x TF32 tensor-core products, fp32 accumulation)."""
     if not x.is_cuda or x.dtype != torch.float32:
         raise RuntimeError("hint_b200.householder_apply: float32 CUDA tensors required (there is no CPU path)")
-    x, W = _dense(x), _dense(W)
+    x, W = x.contiguous(), _dense(W)       # the kernel takes x / y at any 4-byte alignment
     B, d = x.shape
     with torch.cuda.device(x.device):
         y = torch.empty_like(x)

@@ -144,7 +144,7 @@ int hint_adam_step(int32_t n_tensors, float* const* params, const float* const* 
  * log|det| = 0.  FrEIA's source is not part of the reference: published definition, parity-unpinned.  1 <= d <= 128.
  *   hint_householder_matrix           W from Vs (one launch; run once per step when the reflections are trainable)
  *   hint_householder_matrix_backward  dVs [n_reflections,d] from dW and the W the forward produced (no stored intermediates)
- *   hint_householder_apply            y = x W (transpose = 0) or x W^T (transpose != 0), FP32 FFMA; also the input gradient
+ *   hint_householder_apply            y = x W (transpose = 0) or x W^T (transpose != 0), fp32-grade (3 x TF32 split products, fp32 accumulation; error <= 2 x an fp32 GEMM's); any 4-byte alignment; also the input gradient
  *                                     (dx = dy W^T)
  *   hint_householder_wgrad            dW = x^T dy (deterministic two-stage reduction) */
 int hint_householder_matrix(const float* Vs, int32_t n_reflections, int32_t d, float* W, void* stream);

@@ -6,6 +6,8 @@ dev = torch.device("cuda:0")
 for d, B in ((43, 1 << 20), (100, 1 << 18), (8, 1 << 20), (20, 1 << 20)):
     W = householder_matrix(torch.randn(d, d, device=dev))
     x = torch.randn(B, d, device=dev)
+    n = min(B, 1 << 16); yr = x[:n].double() @ W.double(); ya = householder_apply(x, W)[:n].double(); yt = (x[:n] @ W).double()
+    print(f"d={d:3d}: apply max|err| vs fp64 {float((ya - yr).abs().max()):.2e} (torch fp32 matmul: {float((yt - yr).abs().max()):.2e}), max|y| {float(yr.abs().max()):.2f}", flush=True)
     for name, fn in (("apply", lambda: householder_apply(x, W)), ("wgrad", lambda: _wgrad(x, x))):
         for _ in range(2): fn()
         torch.cuda.synchronize()

@@ -212,6 +212,30 @@ def test_householder_kernels_match_the_published_definition(dev, d, n):
         assert float((back - x.to(dev)).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("d", [3, 8, 43, 48, 49, 100])
+def test_householder_apply_ragged_unaligned_and_row_isolation(dev, d):
+    """`hint_householder_apply` (error-compensated 3 x TF32 MMAs): fp32-grade against fp64 for row counts around the 16/32-row
+    ranges, for operands that are not 16-byte aligned (a view starting at row 1), in both directions; a non-finite row stays in its row."""
+    from hint_b200.householder import householder_matrix, householder_apply
+    g = torch.Generator().manual_seed(7 + d)
+    W = householder_matrix(torch.randn(d, d, generator=g).to(dev))
+    base = torch.randn(1001, d, generator=g).to(dev)
+    for B in (1, 15, 16, 17, 31, 33, 1000):
+        for off in (0, 1):
+            x = base[off:off + B]
+            for tr in (False, True):
+                y = householder_apply(x, W, transpose=tr)
+                ref = x.double() @ (W.double().t() if tr else W.double())
+                assert y.shape == (B, d)
+                assert float((y.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), (B, off, tr)
+    x = base[:100].clone()
+    x[40, d // 2] = float("inf")
+    y = householder_apply(x, W)
+    ok = torch.ones(100, dtype=torch.bool, device=dev); ok[40] = False
+    assert bool(torch.isfinite(y[ok]).all())
+    assert float((y[ok].double() - x[ok].double() @ W.double()).abs().max()) <= 1e-5 * 8
+
+
 def test_freia_householder_perm_uses_the_kernels_on_cuda(dev):
     """The shim's HouseholderPerm (fixed and trainable) gives the same numbers on CUDA (library kernels) as on the CPU (plain
     PyTorch definition), forward, reverse and gradients, and launches library kernels."""
