@@ -3,7 +3,7 @@
 // configs/uci_data/miniboone_hint_8.py:60-63 `fixed: True`; configs/plus_shape/unconditional_hint_4_3.py:60-71 `fixed: False`,
 // trainable).  FrEIA's source is not part of the reference: the definition is the published one, parity-unpinned.
 //
-//   hh_matrix_kernel       W from Vs: one CTA, W resident in shared memory, d reflections of O(d^2) each
+//   hh_matrix_kernel       W from Vs: the chain of reflections is row-wise, a warp carries 4 rows of W in registers through it
 //   hh_matrix_bwd_kernel   dVs from dW WITHOUT storing the partial products: reflections are involutions, so the chain is
 //                          walked backwards by W_{k-1} = W_k H_k while dW is pulled back by G_{k-1} = G_k H_k; per reflection
 //                          only matrix-vector products (a = G v, b = W'^T a, c = W' v, e = G^T c):
@@ -25,91 +25,116 @@ namespace {
 constexpr int kHhThreads = 256;
 constexpr int kHhMaxD = 128;
 
-__device__ __forceinline__ float hh_block_sum(float v, float* red) {
+// The reflections act on W from the right, W_k = W_{k-1} (I - 2 v v^T / s): every ROW of W goes through the whole chain on its
+// own, row <- row - (2 (row . v) / s) v.  A warp owns kHhRowsPerWarp rows (lane l holds elements l, l + 32, l + 64, l + 96 of each,
+// d <= 128), the dot products are butterfly reductions and the rows' chains interleave: no barrier, ~60 cycles per reflection
+// instead of three CTA-wide passes over a shared-memory matrix.
+constexpr int kHhRowsPerWarp = 4;
+constexpr int kHhLaneElems = kHhMaxD / 32;
+
+__device__ __forceinline__ float hh_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.f;
+    return v;
+}
+__device__ __forceinline__ void hh_load_v(const float* __restrict__ Vs, int k, int d, int lane, float (&v)[kHhLaneElems]) {
 #pragma unroll
-    for (int w = 0; w < kHhThreads / 32; ++w) r += red[w];
-    return r;
+    for (int m = 0; m < kHhLaneElems; ++m) { const int j = lane + 32 * m; v[m] = j < d ? __ldg(Vs + (size_t)k * d + j) : 0.f; }
+}
+__device__ __forceinline__ float hh_dot(const float (&a)[kHhLaneElems], const float (&b)[kHhLaneElems]) {
+    float p = 0.f;
+#pragma unroll
+    for (int m = 0; m < kHhLaneElems; ++m) p = fmaf(a[m], b[m], p);
+    return hh_warp_sum(p);
 }
 
-// u = M v (rows) or M^T v (cols) for a [d][dp] shared-memory matrix; result in out[0..d)
-__device__ __forceinline__ void hh_matvec(const float* M, const float* v, float* out, int d, int dp, bool transpose) {
-    for (int r = threadIdx.x; r < d; r += kHhThreads) {
-        float a = 0.f;
-        if (!transpose) for (int c = 0; c < d; ++c) a = fmaf(M[r * dp + c], v[c], a);
-        else for (int c = 0; c < d; ++c) a = fmaf(M[c * dp + r], v[c], a);
-        out[r] = a;
-    }
-    __syncthreads();
-}
-// M -= 2 u v^T / s
-__device__ __forceinline__ void hh_rank1(float* M, const float* u, const float* v, float two_over_s, int d, int dp) {
-    for (int i = threadIdx.x; i < d * d; i += kHhThreads) {
-        const int r = i / d, c = i - r * d;
-        M[r * dp + c] = fmaf(-two_over_s * u[r], v[c], M[r * dp + c]);
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(kHhThreads) hh_matrix_kernel(const float* __restrict__ Vs, int n, int d, float* __restrict__ W) {
-    extern __shared__ __align__(16) float sm[];
-    const int dp = d + 1;
-    float* Ws = sm;                 // [d][dp]
-    float* v = Ws + d * dp;         // [d]
-    float* u = v + kHhMaxD;         // [d]
-    float* red = u + kHhMaxD;       // [8]
-    for (int i = threadIdx.x; i < d * d; i += kHhThreads) { const int r = i / d, c = i - r * d; Ws[r * dp + c] = r == c ? 1.f : 0.f; }
-    __syncthreads();
+__global__ void __launch_bounds__(128) hh_matrix_kernel(const float* __restrict__ Vs, int n, int d, float* __restrict__ W) {
+    const int lane = threadIdx.x & 31, r0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kHhRowsPerWarp;
+    if (r0 >= d) return;
+    float row[kHhRowsPerWarp][kHhLaneElems], v[kHhLaneElems], vn[kHhLaneElems];
+#pragma unroll
+    for (int i = 0; i < kHhRowsPerWarp; ++i)
+#pragma unroll
+        for (int m = 0; m < kHhLaneElems; ++m) row[i][m] = (r0 + i == lane + 32 * m) ? 1.f : 0.f;
+    if (n > 0) hh_load_v(Vs, 0, d, lane, vn);
     for (int k = 0; k < n; ++k) {
-        float part = 0.f;
-        for (int c = threadIdx.x; c < d; c += kHhThreads) { const float t = Vs[(size_t)k * d + c]; v[c] = t; part = fmaf(t, t, part); }
-        const float s = hh_block_sum(part, red);
-        hh_matvec(Ws, v, u, d, dp, false);
-        hh_rank1(Ws, u, v, 2.f / s, d, dp);
+#pragma unroll
+        for (int m = 0; m < kHhLaneElems; ++m) v[m] = vn[m];
+        if (k + 1 < n) hh_load_v(Vs, k + 1, d, lane, vn);
+        const float two_over_s = 2.f / hh_dot(v, v);
+        float f[kHhRowsPerWarp];
+#pragma unroll
+        for (int i = 0; i < kHhRowsPerWarp; ++i) f[i] = two_over_s * hh_dot(row[i], v);
+#pragma unroll
+        for (int i = 0; i < kHhRowsPerWarp; ++i)
+#pragma unroll
+            for (int m = 0; m < kHhLaneElems; ++m) row[i][m] = fmaf(-f[i], v[m], row[i][m]);
     }
-    for (int i = threadIdx.x; i < d * d; i += kHhThreads) { const int r = i / d, c = i - r * d; W[i] = Ws[r * dp + c]; }
+#pragma unroll
+    for (int i = 0; i < kHhRowsPerWarp; ++i)
+#pragma unroll
+        for (int m = 0; m < kHhLaneElems; ++m) {
+            const int j = lane + 32 * m;
+            if (r0 + i < d && j < d) W[(size_t)(r0 + i) * d + j] = row[i][m];
+        }
 }
 
-__global__ void __launch_bounds__(kHhThreads) hh_matrix_bwd_kernel(const float* __restrict__ Vs, const float* __restrict__ W,
-                                                                   const float* __restrict__ dW, int n, int d, float* __restrict__ dVs) {
-    extern __shared__ __align__(16) float sm[];
-    const int dp = d + 1;
-    float* Ws = sm;                   // W_k, walked back to W_{k-1}
-    float* Gs = Ws + d * dp;          // G_k
-    float* v = Gs + d * dp;
-    float* a = v + kHhMaxD;
-    float* b = a + kHhMaxD;
-    float* c = b + kHhMaxD;
-    float* e = c + kHhMaxD;
-    float* red = e + kHhMaxD;
-    for (int i = threadIdx.x; i < d * d; i += kHhThreads) {
-        const int r = i / d, cc = i - r * d;
-        Ws[r * dp + cc] = W[i];
-        Gs[r * dp + cc] = dW[i];
-    }
-    __syncthreads();
+// Backward of the chain.  Walking back (k = n-1 .. 0) with W' = W_{k-1} = W_k H_k and G_{k-1} = G_k H_k is again row-wise; what
+// couples the rows is only the OUTPUT dv_k = -2/s (W'^T a + G_k^T c) + 4 (c . a) / s^2 v  with a = G_k v, c = W' v = -W_k v:
+// every warp adds its rows' terms into a shared buffer slot and the first d threads sum the slots in a fixed order
+// (deterministic); the buffer is double-buffered, so ONE CTA barrier per reflection.  One CTA of 32 warps x 4 rows.
+constexpr int kHhBwdWarps = kHhMaxD / kHhRowsPerWarp;
+
+__global__ void __launch_bounds__(32 * kHhBwdWarps) hh_matrix_bwd_kernel(const float* __restrict__ Vs, const float* __restrict__ W,
+                                                                         const float* __restrict__ dW, int n, int d, float* __restrict__ dVs) {
+    __shared__ float P[2][kHhBwdWarps][kHhMaxD];
+    __shared__ float Q[2][kHhBwdWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r0 = warp * kHhRowsPerWarp;
+    const int nwarps = (d + kHhRowsPerWarp - 1) / kHhRowsPerWarp;
+    float wr[kHhRowsPerWarp][kHhLaneElems], gr[kHhRowsPerWarp][kHhLaneElems], v[kHhLaneElems], vn[kHhLaneElems];
+#pragma unroll
+    for (int i = 0; i < kHhRowsPerWarp; ++i)
+#pragma unroll
+        for (int m = 0; m < kHhLaneElems; ++m) {
+            const int j = lane + 32 * m;
+            const bool in = r0 + i < d && j < d;
+            wr[i][m] = in ? W[(size_t)(r0 + i) * d + j] : 0.f;
+            gr[i][m] = in ? dW[(size_t)(r0 + i) * d + j] : 0.f;
+        }
+    if (n > 0) hh_load_v(Vs, n - 1, d, lane, vn);
     for (int k = n - 1; k >= 0; --k) {
-        float part = 0.f;
-        for (int q = threadIdx.x; q < d; q += kHhThreads) { const float t = Vs[(size_t)k * d + q]; v[q] = t; part = fmaf(t, t, part); }
-        const float s = hh_block_sum(part, red);
-        // W_{k-1} = W_k H_k  (H_k is its own inverse)
-        hh_matvec(Ws, v, c, d, dp, false);          // c = W_k v  (temporarily)
-        hh_rank1(Ws, c, v, 2.f / s, d, dp);
-        hh_matvec(Gs, v, a, d, dp, false);          // a = G_k v
-        hh_matvec(Ws, a, b, d, dp, true);           // b = W_{k-1}^T a = M v
-        hh_matvec(Ws, v, c, d, dp, false);          // c = W_{k-1} v
-        hh_matvec(Gs, c, e, d, dp, true);           // e = G_k^T c = M^T v
-        float pd = 0.f;
-        for (int q = threadIdx.x; q < d; q += kHhThreads) pd = fmaf(c[q], a[q], pd);
-        const float vMv = hh_block_sum(pd, red);
-        for (int q = threadIdx.x; q < d; q += kHhThreads)
-            dVs[(size_t)k * d + q] = -2.f / s * (b[q] + e[q]) + 4.f * vMv / (s * s) * v[q];
-        hh_rank1(Gs, a, v, 2.f / s, d, dp);         // G_{k-1} = G_k H_k
+        const int slot = k & 1;
+#pragma unroll
+        for (int m = 0; m < kHhLaneElems; ++m) v[m] = vn[m];
+        if (k > 0) hh_load_v(Vs, k - 1, d, lane, vn);
+        const float s = hh_dot(v, v), two_over_s = 2.f / s;
+        if (warp < nwarps) {
+            float c0[kHhRowsPerWarp], a[kHhRowsPerWarp];
+#pragma unroll
+            for (int i = 0; i < kHhRowsPerWarp; ++i) { c0[i] = hh_dot(wr[i], v); a[i] = hh_dot(gr[i], v); }
+            float p[kHhLaneElems] = {}, q = 0.f;
+#pragma unroll
+            for (int i = 0; i < kHhRowsPerWarp; ++i) {
+                const float c = -c0[i];                                // W_{k-1} v = W_k H_k v = -W_k v
+                q = fmaf(c, a[i], q);
+#pragma unroll
+                for (int m = 0; m < kHhLaneElems; ++m) {
+                    wr[i][m] = fmaf(-two_over_s * c0[i], v[m], wr[i][m]);   // row of W_{k-1}
+                    p[m] = fmaf(a[i], wr[i][m], fmaf(c, gr[i][m], p[m]));   // a W'^T + c G_k^T terms
+                    gr[i][m] = fmaf(-two_over_s * a[i], v[m], gr[i][m]);    // row of G_{k-1}
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < kHhLaneElems; ++m) P[slot][warp][lane + 32 * m] = p[m];
+            if (lane == 0) Q[slot][warp] = q;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < d) {
+            float bp = 0.f, vMv = 0.f;
+            for (int w = 0; w < nwarps; ++w) { bp += P[slot][w][threadIdx.x]; vMv += Q[slot][w]; }
+            const float vj = __ldg(Vs + (size_t)k * d + threadIdx.x);
+            dVs[(size_t)k * d + threadIdx.x] = -two_over_s * bp + 4.f * vMv / (s * s) * vj;
+        }
     }
 }
 
@@ -306,19 +331,14 @@ int hh_max_d() { return kHhMaxD; }
 
 cudaError_t hh_matrix(const float* Vs, int n, int d, float* W, cudaStream_t st) {
     if (d < 1 || d > kHhMaxD || n < 0) return cudaErrorInvalidValue;
-    const size_t smem = sizeof(float) * ((size_t)d * (d + 1) + 2 * kHhMaxD + 8);
-    cudaError_t e = cudaFuncSetAttribute((const void*)hh_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hh_matrix_kernel<<<1, kHhThreads, smem, st>>>(Vs, n, d, W); HINT_LAUNCHED();
+    const int rows_per_cta = 4 * kHhRowsPerWarp;       // 4 warps
+    hh_matrix_kernel<<<(d + rows_per_cta - 1) / rows_per_cta, 128, 0, st>>>(Vs, n, d, W); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
 cudaError_t hh_matrix_backward(const float* Vs, const float* W, const float* dW, int n, int d, float* dVs, cudaStream_t st) {
     if (d < 1 || d > kHhMaxD || n < 0) return cudaErrorInvalidValue;
-    const size_t smem = sizeof(float) * (2 * (size_t)d * (d + 1) + 5 * kHhMaxD + 8);
-    cudaError_t e = cudaFuncSetAttribute((const void*)hh_matrix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hh_matrix_bwd_kernel<<<1, kHhThreads, smem, st>>>(Vs, W, dW, n, d, dVs); HINT_LAUNCHED();
+    hh_matrix_bwd_kernel<<<1, 32 * kHhBwdWarps, 0, st>>>(Vs, W, dW, n, d, dVs); HINT_LAUNCHED();
     return cudaGetLastError();
 }
 
