@@ -514,7 +514,7 @@ def run_ours(args, w, name):
                 modes[md] = {"error": str(e)[:200]}
         line["modes"] = modes
         # the configs' full x-lane: the same blocks with the inter-block HouseholderPerm mixing between them (SURVEY.md 8f-2;
-        # uci configs: fixed reflections, plus_shape hint_4_3: trainable) - FP32 FFMA kernels of this library, not cuBLAS
+        # uci configs: fixed reflections, plus_shape hint_4_3: trainable) - kernels of this library (householder.cu), not cuBLAS
         hh = {}
         for kind in ("fixed", "trainable"):
             try:
@@ -539,6 +539,13 @@ def run_ours(args, w, name):
                 entry["train_tflops_algorithmic"] = 3 * ph["flops_per_sample_fwd"] * ph["train_samples_per_s"] / 1e12
                 entry["train_frac_of_tf32_peak"] = entry["train_tflops_algorithmic"] / peak_step
                 entry["fwd_frac_of_tf32_peak"] = ph["flops_per_sample_fwd"] * ph["fwd_logdet_samples_per_s"] / 1e12 / peak_step
+                # the same model with the config's own inter-block HouseholderPerm (plus_shape hint_4_3: trainable reflections,
+                # configs/plus_shape/unconditional_hint_4_3.py:60-71; uci / lens hint_8: fixed)
+                kind = "trainable" if wn.startswith("plus") else "fixed"
+                ph, keep = phases(wl, Bw, args.mode, 3, 3, householder=kind)
+                del keep
+                entry["with_householder"] = {"kind": kind, "train_samples_per_s": ph["train_samples_per_s"], "train_ms": ph["train_ms"],
+                                             "launches_per_train_step": ph["launches_per_train_step"]}
                 cfgs.append(entry)
             except Exception as e:
                 cfgs.append({"workload": wn, "batch": Bw, "error": str(e)[:200]})
