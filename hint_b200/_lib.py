@@ -133,3 +133,26 @@ def check(rc):
     if rc == HINT_ERR_INVALID:
         raise ValueError("hint_b200: " + msg)
     raise RuntimeError(f"hint_b200 (code {rc}): {msg}")
+
+
+# ---- cheap device guard / stream lookup (torch.cuda.device + torch.cuda.current_stream cost ~20 us per call pair in Python,
+# which is what bounds a small-batch step through the autograd wrappers) ----------------------------------------------------------
+import contextlib as _contextlib
+
+_NULL_CTX = _contextlib.nullcontext()
+
+
+def on_device(device):
+    """Context manager making ``device`` the current CUDA device; a no-op object when it already is."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NULL_CTX
+    return torch.cuda.device(idx)
+
+
+def stream_of(device):
+    """Raw cudaStream_t of torch's current stream on ``device``."""
+    import torch
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice() if idx is None else idx)

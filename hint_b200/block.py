@@ -76,6 +76,7 @@ class TreePlan:
         _lib.check(lib.hint_plan_create(int(d), int(dc), ci, len(c_internal), float(clamp), int(max_splits),
                                         int(min_split_size), 1 if reshuffle else 0, ctypes.byref(handle)))
         self._h = handle
+        self._ws_cache = {}
         self.d, self.dc, self.clamp = int(d), int(dc), float(clamp)
         self.c_internal, self.max_splits, self.min_split_size = [int(v) for v in c_internal], int(max_splits), int(min_split_size)
         n = lib.hint_plan_num_nodes(handle)
@@ -122,6 +123,15 @@ class TreePlan:
         return bool(self._lib.hint_plan_mode_supported(self._h, _MODES[mode]))
 
     # -- launches ------------------------------------------------------------------------------
+    def _ws_bytes(self, B, kind):
+        key = (B, kind)
+        n = self._ws_cache.get(key)
+        if n is None:
+            if len(self._ws_cache) > 64:
+                self._ws_cache.clear()
+            n = self._ws_cache[key] = self._lib.hint_workspace_bytes(self._h, B, kind)
+        return n
+
     @staticmethod
     def _check(t, name, shape=None):
         if t is None:
@@ -155,14 +165,14 @@ class TreePlan:
             c = self._dense16(c)
         x = self._dense16(x)
         flat = self._dense16(flat)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             z = torch.empty_like(x)
             J = torch.empty(B, dtype=torch.float32, device=x.device)
-            nbytes = self._lib.hint_workspace_bytes(self._h, B, _lib.WS_FORWARD)
+            nbytes = self._ws_bytes(B, _lib.WS_FORWARD)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             _lib.check(self._lib.hint_forward(self._h, x.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(), B,
                                               1 if rev else 0, _MODES[mode or _mode], z.data_ptr(), J.data_ptr(),
-                                              ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+                                              ws.data_ptr(), nbytes, _lib.stream_of(x.device)))
         return z, J
 
     def backward(self, z, c, flat, dz, dJ, mode=None, want_xrec=False, want_dc=True, nll_scale=None, out=None):
@@ -192,17 +202,17 @@ class TreePlan:
             self._check(c, "c", (B, self.dc))
             c = self._dense16(c)
         z, dz, dJ, flat = self._dense16(z), self._dense16(dz), self._dense16(dJ), self._dense16(flat)
-        with torch.cuda.device(z.device):
+        with _lib.on_device(z.device):
             dx = torch.empty_like(z)
             dc = torch.empty(B, self.dc, dtype=torch.float32, device=z.device) if (self.dc and want_dc) else None
             xrec = torch.empty_like(z) if want_xrec else None
             dflat = out if (out is not None and out.is_contiguous() and out.data_ptr() % 16 == 0 and out.shape == flat.shape) else torch.empty_like(flat)
-            nbytes = self._lib.hint_workspace_bytes(self._h, B, _lib.WS_BACKWARD)
+            nbytes = self._ws_bytes(B, _lib.WS_BACKWARD)
             if nbytes == 0:
                 _lib.check(_lib.HINT_ERR_CUDA)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
             tail = (xrec.data_ptr() if want_xrec else None, dx.data_ptr(), dc.data_ptr() if dc is not None else None,
-                    dflat.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+                    dflat.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_of(z.device))
             if nll_scale is not None:
                 _lib.check(self._lib.hint_backward_nll(self._h, z.data_ptr(), c.data_ptr() if self.dc else None, flat.data_ptr(),
                                                        dz.data_ptr() if dz is not None else None, nll_scale, B, _MODES[mode or _mode], *tail))

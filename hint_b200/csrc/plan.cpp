@@ -292,8 +292,10 @@ std::string build_plan(Plan& p, int d, int dc, const int32_t* c_internal, int n_
     if (p.n_params > (int64_t)1 << 30) return "parameter count too large";
     build_packed_layout(p);
     int tm_f = 0, tm_b = 0;
+#ifdef HINT_B200_DEV   // tile-size overrides (developer builds only)
     if (const char* e = std::getenv("HINT_B200_TM_FWD")) tm_f = std::atoi(e);
     if (const char* e = std::getenv("HINT_B200_TM_BWD")) tm_b = std::atoi(e);
+#endif
     *code = HINT_ERR_UNSUPPORTED;
     std::string err = build_schedule(p, p.fwd, false, tm_f);
     if (!err.empty()) return err;

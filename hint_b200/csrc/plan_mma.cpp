@@ -408,8 +408,10 @@ void build_mma_plan(const Plan& p, MmaPlan& m) {
     std::vector<NodeOps> ops;
     pack_nodes(p, m, ops);
     int tm_f = 0, tm_b = 0;
+#ifdef HINT_B200_DEV   // tile-size overrides (developer builds only)
     if (const char* e = std::getenv("HINT_B200_MMA_TM_FWD")) tm_f = std::atoi(e);
     if (const char* e = std::getenv("HINT_B200_MMA_TM_BWD")) tm_b = std::atoi(e);
+#endif
     std::string err = build_mschedule(p, m, ops, m.fwd, false, tm_f);
     if (err.empty()) err = build_mschedule(p, m, ops, m.bwd, true, tm_b);
     if (!err.empty()) { m.ok = false; m.why = err; return; }

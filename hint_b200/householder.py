@@ -9,7 +9,7 @@ from . import _lib
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())   # inside _lib.on_device(...)
 
 
 def _dense(t):
@@ -23,7 +23,7 @@ def householder_matrix(Vs):
         raise RuntimeError("hint_b200.householder_matrix: float32 CUDA tensor required (there is no CPU path)")
     Vs = _dense(Vs.detach())
     n, d = Vs.shape
-    with torch.cuda.device(Vs.device):
+    with _lib.on_device(Vs.device):
         W = torch.empty(d, d, dtype=torch.float32, device=Vs.device)
         _lib.check(_lib.load().hint_householder_matrix(Vs.data_ptr(), n, d, W.data_ptr(), _stream()))
     return W
@@ -35,7 +35,7 @@ def householder_apply(x, W, transpose=False):
         raise RuntimeError("hint_b200.householder_apply: float32 CUDA tensors required (there is no CPU path)")
     x, W = x.contiguous(), _dense(W)       # the kernel takes x / y at any 4-byte alignment
     B, d = x.shape
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         y = torch.empty_like(x)
         _lib.check(_lib.load().hint_householder_apply(x.data_ptr(), W.data_ptr(), B, d, 1 if transpose else 0, y.data_ptr(), _stream()))
     return y
@@ -45,7 +45,7 @@ def _wgrad(x, dz):
     lib = _lib.load()
     x, dz = _dense(x), _dense(dz)
     B, d = x.shape
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         dW = torch.empty(d, d, dtype=torch.float32, device=x.device)
         nbytes = lib.hint_householder_wgrad_workspace_bytes(d)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
@@ -59,7 +59,7 @@ def householder_vs_grad(x, dy, Vs, W, out=None):
     dW = _wgrad(x, dy)
     V = _dense(Vs.detach())
     n, d = V.shape
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         dVs = out if (out is not None and out.is_contiguous() and out.data_ptr() % 16 == 0) else torch.empty_like(V)
         _lib.check(_lib.load().hint_householder_matrix_backward(V.data_ptr(), _dense(W).data_ptr(), dW.data_ptr(), n, d, dVs.data_ptr(), _stream()))
         if out is not None and dVs is not out:
@@ -90,7 +90,7 @@ class HouseholderMix(torch.autograd.Function):
             lib = _lib.load()
             V = _dense(Vs.detach())
             n, d = V.shape
-            with torch.cuda.device(x.device):
+            with _lib.on_device(x.device):
                 dVs = torch.empty_like(V)
                 _lib.check(lib.hint_householder_matrix_backward(V.data_ptr(), W.data_ptr(), dW.data_ptr(), n, d, dVs.data_ptr(), _stream()))
         return dx, dVs, None, None

@@ -20,7 +20,7 @@ from .householder import householder_apply, householder_matrix, householder_vs_g
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())   # inside _lib.on_device(...)
 
 
 def add_noise(x, sigma, seed, offset=0, out=None):
@@ -32,7 +32,7 @@ def add_noise(x, sigma, seed, offset=0, out=None):
         x = x.clone()
     if out is None:
         out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         _lib.check(_lib.load().hint_add_noise(x.data_ptr(), out.data_ptr(), x.numel(), float(sigma), int(seed) & (2 ** 64 - 1),
                                               int(offset) & (2 ** 64 - 1), _stream()))
     return out
@@ -52,7 +52,7 @@ def nll_loss_fused(z, logdet):
     if any(tuple(j.shape) != (B,) or j.dtype != torch.float32 or not j.is_cuda for j in js):
         raise ValueError("hint_b200.nll_loss_fused: every logdet must be a float32 CUDA tensor of shape [B]")
     jp = (ctypes.c_void_p * len(js))(*[j.data_ptr() for j in js])
-    with torch.cuda.device(z.device):
+    with _lib.on_device(z.device):
         out = torch.empty(3, dtype=torch.float32, device=z.device)
         nbytes = lib.hint_nll_workspace_bytes()
         ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
@@ -91,7 +91,7 @@ class FusedClampAdam(torch.optim.Optimizer):
             arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
             sizes = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
-            with torch.cuda.device(ps[0].device):
+            with _lib.on_device(ps[0].device):
                 _lib.check(lib.hint_adam_step(n, arr(ps), arr([p.grad for p in ps]), arr([self.state[p]["exp_avg"] for p in ps]),
                                               arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes, float(group["lr"]), float(b1),
                                               float(b2), float(group["eps"]), float(group["weight_decay"]),
