@@ -5,7 +5,12 @@ configs/lens_shape/conditional_hint_8_full.py:78-89; the `*_inn_*` / `*_cinn_*` 
 FrEIA's source is not part of the reference and no version is pinned, so these follow the published FrEIA definitions of
 that period - **parity-unpinned** (DESIGN.md section 2): a four-layer fully connected subnet, a single affine transformation
 of the lower half (AffineCoupling) or of the whole input driven by the condition alone (ExternalAffineCoupling), with the
-same soft clamp hint.py:56-60 uses, e(s) = exp(clamp * 0.636 * atan(s)).  Plain PyTorch: off the hot path (ndim_y = 2 / 4)."""
+same soft clamp hint.py:56-60 uses, e(s) = exp(clamp * 0.636 * atan(s)).
+
+On CUDA float32 tensors both couplings run on the library's fused kernels (hint_b200/csrc/mlp_coupling.cu through
+hint_b200.coupling: one launch forward, two backward); the plain-PyTorch expressions below are the definition, the CPU path of
+this test shim, the checker of the kernels, and the fallback for what the kernels do not cover (custom subnets, dropout in
+training mode, gradients through rev=True, widths outside the envelope)."""
 import torch
 import torch.nn as nn
 
@@ -43,6 +48,23 @@ class _AffineBase(nn.Module):
     def e(self, s):
         return torch.exp(self.log_e(s))
 
+    def _fused(self, u, v, rev):
+        """(y, logdet) from the fused kernels, or None when this call is outside what they cover."""
+        if not (u.is_cuda and v.is_cuda and u.dtype == torch.float32 and v.dtype == torch.float32):
+            return None
+        s, t = self.s, self.t
+        if type(s) is not F_fully_connected or type(t) is not F_fully_connected:
+            return None
+        if self.training and (s.d1.p > 0 or t.d1.p > 0):
+            return None
+        from hint_b200 import coupling as _k
+        params = _k.subnet_params(s, t)
+        if rev and torch.is_grad_enabled() and (u.requires_grad or v.requires_grad or any(p.requires_grad for p in params)):
+            return None
+        if not _k.supported(u.shape[1], v.shape[1], s.fc1.out_features):
+            return None
+        return _k.MlpCouplingFn.apply(u, v, self.clamp, bool(rev), *params)
+
     def jacobian(self, x, c=[], rev=False):
         """Cached log|det J| of the last call (as hint.py:128-129 does), so ``jacobian(None)`` works (train_conditional.py:50-55)."""
         return self.jac
@@ -70,6 +92,10 @@ class AffineCoupling(_AffineBase):
     def forward(self, x, c=[], rev=False):
         x1, x2 = x[0].narrow(1, 0, self.split_len1), x[0].narrow(1, self.split_len1, self.split_len2)
         x1_c = torch.cat([x1, *c], 1) if self.conditional else x1
+        fused = self._fused(x1_c, x2, rev) if x[0].dim() == 2 else None
+        if fused is not None:
+            y2, self.jac = fused
+            return [torch.cat((x1, y2), 1)]
         s, t = self.s(x1_c), self.t(x1_c)
         if not rev:
             y2 = self.e(s) * x2 + t
@@ -92,7 +118,11 @@ class ExternalAffineCoupling(_AffineBase):
         self.t = F_class(condition_length, channels, **F_args)
 
     def forward(self, x, c=[], rev=False):
-        cc = torch.cat(list(c), 1)
+        cc = torch.cat(list(c), 1) if len(c) > 1 else c[0]
+        fused = self._fused(cc, x[0], rev) if x[0].dim() == 2 else None
+        if fused is not None:
+            y, self.jac = fused
+            return [y]
         s, t = self.s(cc), self.t(cc)
         if not rev:
             y = self.e(s) * x[0] + t

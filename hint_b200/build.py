@@ -27,7 +27,8 @@ UNITS = {
     "mma_launch.cu": ["launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "mma_kernels.cuh", HDR_API],
     "train_ops.cu": ["train_ops.h", "launch_count.h", HDR_API],
     "householder.cu": ["householder.h", "launch_count.h", HDR_API],
-    "capi.cu": ["train_ops.h", "householder.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 
+    "mlp_coupling.cu": ["mlp_coupling.h", "launch_count.h", HDR_API],
+    "capi.cu": ["train_ops.h", "householder.h", "mlp_coupling.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 
                 "simt_phases.cuh", "simt_kernels.cuh", HDR_API],
 }
 NVCC_FLAGS = ["-O3", "-std=c++17", "-DHINT_MMA_MINB=2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]

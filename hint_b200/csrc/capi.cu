@@ -20,6 +20,7 @@
 #include "tc3_launch.h"
 #include "train_ops.h"
 #include "householder.h"
+#include "mlp_coupling.h"
 #include "simt_kernels.cuh"
 
 using namespace hint;
@@ -589,7 +590,7 @@ int hint_householder_matrix_backward(const float* Vs, const float* W, const floa
 
 int hint_householder_apply(const float* x, const float* W, int64_t B, int32_t d, int32_t transpose, float* y, void* stream) {
     if (B < 0 || d < 1 || d > hh_max_d() || (B > 0 && (!x || !W || !y))) return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
-    if (y == x) return fail(HINT_ERR_INVALID, "y must not alias x");
+    if (B > 0 && y == x) return fail(HINT_ERR_INVALID, "y must not alias x");
     CUDA_TRY(hh_apply(x, W, (long long)B, d, transpose, y, (cudaStream_t)stream));
     return HINT_OK;
 }
@@ -601,6 +602,34 @@ int hint_householder_wgrad(const float* x, const float* dz, int64_t B, int32_t d
     if (B < 0 || d < 1 || d > hh_max_d() || !dW || (B > 0 && (!x || !dz))) return fail(HINT_ERR_INVALID, "bad Householder arguments (1 <= d <= 128)");
     if (!workspace || workspace_bytes < hh_wgrad_workspace_bytes(d)) return fail(HINT_ERR_WORKSPACE, "workspace too small");
     CUDA_TRY(hh_wgrad(x, dz, (long long)B, d, dW, workspace, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+int hint_mlp_coupling_supported(int32_t du, int32_t dv, int32_t hidden) { return mc_supported(du, dv, hidden) ? 1 : 0; }
+
+int hint_mlp_coupling_forward(const float* u, int32_t du, const float* v, int32_t dv, int32_t hidden, const float* const* params, float clamp,
+                              int32_t rev, int64_t B, float* y, float* logdet, void* stream) {
+    if (!mc_supported(du, dv, hidden)) return fail(HINT_ERR_UNSUPPORTED, "coupling outside the fused kernel's envelope (du, dv <= 128, hidden <= 256)");
+    if (B < 0 || !params || (B > 0 && (!u || !v || !y || !logdet))) return fail(HINT_ERR_INVALID, "bad coupling arguments");
+    for (int i = 0; i < 16; ++i) if (!params[i]) return fail(HINT_ERR_INVALID, "null parameter pointer");
+    if (B > 0 && y == v) return fail(HINT_ERR_INVALID, "y must not alias v");
+    CUDA_TRY(mc_forward(u, du, v, dv, hidden, params, clamp, rev ? 1 : 0, (long long)B, y, logdet, (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+size_t hint_mlp_coupling_workspace_bytes(int32_t du, int32_t dv, int32_t hidden, int64_t B) {
+    return mc_supported(du, dv, hidden) && B >= 0 ? mc_workspace_bytes(du, dv, hidden, (long long)B) : 0;
+}
+
+int hint_mlp_coupling_backward(const float* u, int32_t du, const float* v, int32_t dv, int32_t hidden, const float* const* params, float clamp,
+                               int64_t B, const float* dy, const float* dlogdet, float* du_grad, float* dv_grad, float* const* dparams,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!mc_supported(du, dv, hidden)) return fail(HINT_ERR_UNSUPPORTED, "coupling outside the fused kernel's envelope (du, dv <= 128, hidden <= 256)");
+    if (B < 0 || !params || !dparams || (B > 0 && (!u || !v || !dy || !du_grad || !dv_grad))) return fail(HINT_ERR_INVALID, "bad coupling arguments");
+    for (int i = 0; i < 16; ++i) if (!params[i] || !dparams[i]) return fail(HINT_ERR_INVALID, "null parameter pointer");
+    if (!workspace || workspace_bytes < mc_workspace_bytes(du, dv, hidden, (long long)B)) return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    CUDA_TRY(mc_backward(u, du, v, dv, hidden, params, clamp, (long long)B, dy, dlogdet, du_grad, dv_grad, dparams, workspace, workspace_bytes,
+                         (cudaStream_t)stream));
     return HINT_OK;
 }
 

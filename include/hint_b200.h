@@ -155,6 +155,26 @@ size_t hint_householder_wgrad_workspace_bytes(int32_t d);
 int hint_householder_wgrad(const float* x, const float* dz, int64_t B, int32_t d, float* dW, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- baseline couplings of the 2-lane conditional configs ------------------------------------------------
+ * FrEIA `AffineCoupling` / `ExternalAffineCoupling` with `F_fully_connected` subnets (fc1-ReLU-fc2-ReLU-fc2b-ReLU-fc3), as
+ * configs/lens_shape/conditional_hint_8_full.py:78-89 places them either side of the HINT block.  FrEIA's source is not part of
+ * the reference: published definition, parity-unpinned; the checker is the plain-PyTorch statement in FrEIA/modules/coupling.py.
+ *     y = e(s(u)) * v + t(u),  logdet = sum_c log e(s_c),  e(s) = exp(clamp * 0.636 * atan(s))     (rev: y = (v - t(u)) / e(s(u)))
+ * u [B,du]: the subnets' input (x1 | condition, or the condition alone); v [B,dv]: the transformed part; hidden: internal_size.
+ * params / dparams: 16 device pointers = [s-net, t-net] x [fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc2b.weight, fc2b.bias,
+ * fc3.weight, fc3.bias], weights in PyTorch's [out][in] row-major layout (the modules' own tensors: no repacking).
+ * Envelope: du, dv <= 128, hidden <= 256 (hint_mlp_coupling_supported).  fp32-grade arithmetic (error-compensated 3 x TF32
+ * tensor-core products, fp32 accumulation).  One launch forward; backward (rev = 0 direction) = one fused launch + one
+ * weight-gradient launch (+ a fixed-order reduction over sample splits when the layers are small): deterministic, no atomics;
+ * dlogdet may be NULL (= 0).  Pointers need 4-byte alignment only. */
+int hint_mlp_coupling_supported(int32_t du, int32_t dv, int32_t hidden);
+int hint_mlp_coupling_forward(const float* u, int32_t du, const float* v, int32_t dv, int32_t hidden, const float* const* params,
+                              float clamp, int32_t rev, int64_t B, float* y, float* logdet, void* stream);
+size_t hint_mlp_coupling_workspace_bytes(int32_t du, int32_t dv, int32_t hidden, int64_t B);
+int hint_mlp_coupling_backward(const float* u, int32_t du, const float* v, int32_t dv, int32_t hidden, const float* const* params,
+                               float clamp, int64_t B, const float* dy, const float* dlogdet, float* du_grad, float* dv_grad,
+                               float* const* dparams, void* workspace, size_t workspace_bytes, void* stream);
+
 const char* hint_last_error(void);
 /* "hint_b200 <version> sm_100a" — lets the host check it loaded the in-tree build */
 const char* hint_version(void);
