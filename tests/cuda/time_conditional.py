@@ -26,6 +26,7 @@ def build(two_lane):
         if p.requires_grad: p.data = 0.005 * torch.randn_like(p)
     return m
 def step(m, x, y):
+    m.zero_grad(set_to_none=True)
     z_y, z_x = m([y, x])
     J = m.log_jacobian(run_forward=False)
     loss = 0.5 * (z_y.pow(2).sum(1) + z_x.pow(2).sum(1)).mean() - J.mean()
@@ -47,3 +48,12 @@ for two in (True, False):
     with torch.no_grad(): ms_f = t(lambda: m([y, x]))
     print(f"B={B} {'two-lane (ExternalAffineCoupling + AffineCoupling)' if two else 'x-lane HINT blocks + y-lane AffineCoupling only'}: "
           f"fwd+bwd {ms:.3f} ms, forward only {ms_f:.3f} ms, library launches per step {(n1 - n0) / 13:.0f}", flush=True)
+if len(sys.argv) > 2:   # host profile of the two-lane step
+    import cProfile, pstats
+    m = build(True)
+    for _ in range(5): step(m, x, y)
+    torch.cuda.synchronize()
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(50): step(m, x, y)
+    torch.cuda.synchronize(); pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(28)
