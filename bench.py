@@ -550,6 +550,12 @@ def run_ours(args, w, name):
             except Exception as e:
                 cfgs.append({"workload": wn, "batch": Bw, "error": str(e)[:200]})
         line["configs"] = cfgs
+        # the 2-lane conditional model of configs/lens_shape/conditional_hint_8_full.py:61-102 through the FrEIA shim exactly as
+        # train_conditional.py:119-156 drives it (autograd, both lanes, fused couplings + Householder + HINT kernels): SURVEY.md 8f-4
+        try:
+            line["conditional_2lane"] = conditional_2lane(torch, dev, launches, 10000)
+        except Exception as e:
+            line["conditional_2lane"] = {"error": str(e)[:200]}
         hint_b200.set_precision(args.mode)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -566,6 +572,51 @@ def run_ours(args, w, name):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+def conditional_2lane(torch, dev, launches, B, ndim_x=20, ndim_y=2, n_blocks=8, h=68):
+    """fwd+bwd of the lens `conditional_hint_8_full` architecture (x lane: HouseholderPerm, HINT block, ExternalAffineCoupling;
+    y lane: HouseholderPerm, AffineCoupling) built through the FrEIA shim; ms per step and library launches per step."""
+    from FrEIA.framework import InputNode, Node, OutputNode, ReversibleGraphNet
+    from FrEIA.modules import (HierarchicalAffineCouplingBlock, HouseholderPerm, AffineCoupling, ExternalAffineCoupling,
+                               F_fully_connected)
+    y_lane, x_lane = [InputNode(ndim_y, name="y")], [InputNode(ndim_x, name="x")]
+    for i in range(n_blocks):
+        if i > 0:
+            y_lane.append(Node(y_lane[-1], HouseholderPerm, {"fixed": True, "n_reflections": ndim_y}, name=f"perm_y_{i}"))
+            x_lane.append(Node(x_lane[-1], HouseholderPerm, {"fixed": True, "n_reflections": ndim_x}, name=f"perm_x_{i}"))
+        x_lane.append(Node(x_lane[-1], HierarchicalAffineCouplingBlock, {"c_internal": [h, h // 2, h // 4, h // 4]}, name=f"hac_x_{i+1}"))
+        x_lane.append(Node(x_lane[-1], ExternalAffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": h}},
+                           conditions=y_lane[-1], name=f"ac_y_to_x_{i+1}"))
+        y_lane.append(Node(y_lane[-1], AffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": h // 4}}, name=f"ac_y_{i+1}"))
+    y_lane.append(OutputNode(y_lane[-1], name="z_y"))
+    x_lane.append(OutputNode(x_lane[-1], name="z_x"))
+    m = ReversibleGraphNet(y_lane + x_lane, verbose=False).to(dev)
+    for p in m.parameters():
+        if p.requires_grad:
+            p.data = 0.005 * torch.randn_like(p)
+    x, y = torch.randn(B, ndim_x, device=dev), torch.randn(B, ndim_y, device=dev)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        z_y, z_x = m([y, x])
+        J = m.log_jacobian(run_forward=False)
+        (0.5 * (z_y.pow(2).sum(1) + z_x.pow(2).sum(1)).mean() - J.mean()).backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n0 = launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    return {"workload": "lens conditional_hint_8_full (2 lanes, 8 blocks), forward + backward through the FrEIA shim", "batch": B,
+            "step_ms": ms, "samples_per_s": B / (ms * 1e-3), "library_launches_per_step": (launches() - n0) // 10,
+            "note": "host-bound: Python graph runtime + autograd; the couplings, mixings and HINT blocks are library kernels"}
 
 def main():
     ap = argparse.ArgumentParser()
