@@ -19,8 +19,5 @@ for name, du, dv, H, B in (("lens ext", 2, 20, 68, 10000), ("lens y", 1, 1, 17, 
     u = torch.randn(B, du, device=dev); v = torch.randn(B, dv, device=dev); dy = torch.randn(B, dv, device=dev); dj = torch.randn(B, device=dev)
     f = t(lambda: K.forward(u, v, params, 5.0))
     b = t(lambda: K.backward(u, v, params, 5.0, dy, dj))
-    def eager():
-        x = v.clone().requires_grad_(True)
-        y = ExternalAffineCoupling.forward.__wrapped__(m, [x], [u]) if hasattr(ExternalAffineCoupling.forward, "__wrapped__") else None
     flops = 2 * 2 * (du * H + 2 * H * H + H * dv) * B
     print(f"{name:12s} du={du} dv={dv} H={H} B={B}: fused forward {f*1e3:.1f} us ({flops/f/1e9:.1f} TFLOP/s), backward (2 launches) {b*1e3:.1f} us ({2*flops/b/1e9:.1f} TFLOP/s)", flush=True)
