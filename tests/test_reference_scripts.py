@@ -145,6 +145,25 @@ def test_train_conditional_runs_unmodified_on_the_two_lane_lens_config(reference
     assert x.shape == (5, 20) and float((x2 - x).abs().max()) < 1e-3 and float((y2 - y).abs().max()) < 1e-4
 
 
+def test_rejection_sampling_imports_unmodified_and_its_mmd_runs(reference_env, monkeypatch):
+    """rejection_sampling.py (the evaluation script north_star names): imports under the environment stubs (data.py, scipy, tqdm,
+    matplotlib) with nothing of this repo on its path but the shim; its `multi_mmd` (rejection_sampling.py:56-73) is run on CPU
+    tensors (`.cuda()` is the identity here) and compared with a direct evaluation of the same inverse-multiquadric estimator."""
+    run_reference, work = reference_env
+    run_reference.prepare_imports(REFERENCE)
+    os.chdir(work)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    rs = importlib.import_module("rejection_sampling")
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(64, 5, generator=g), 0.5 + torch.randn(64, 5, generator=g)
+    got = float(rs.multi_mmd(x, y))
+    d2 = lambda a, b: torch.cdist(a.double(), b.double()).pow(2)
+    k = lambda dd: sum(C ** a * ((C + dd) / a) ** -a for C, a in [(0.5, 1), (0.2, 1), (0.2, 0.5)])
+    want = float((k(d2(x, x)) + k(d2(y, y)) - 2 * k(d2(x, y))).mean())
+    assert abs(got - want) < 1e-4 * max(1.0, abs(want))
+    assert float(rs.multi_mmd(x, x)) < 1e-5 < got
+
+
 CONFIG_DIRS = ["configs/uci_data", "configs/lens_shape", "configs/plus_shape"]
 
 
