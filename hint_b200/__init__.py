@@ -7,11 +7,11 @@ from .block import (HierarchicalAffineCouplingBlock, HierarchicalAffineCouplingT
                     linear_subnet_constructor, set_precision, get_precision, set_backward_check, get_backward_check)
 from .model import HintFlow, GraphedFlow, nll_loss
 from .parallel import BucketedGradAllReduce, broadcast_parameters, shard_rows
-from .train import FusedClampAdam, FusedTrainStep, add_noise, nll_loss_fused
+from .train import FusedClampAdam, FusedTrainStep, add_noise, nll_loss_fused, multi_mmd
 
 __version__ = _lib.load().hint_version().decode()
 
 __all__ = ["HierarchicalAffineCouplingBlock", "HierarchicalAffineCouplingTree", "TreePlan",
            "linear_subnet_constructor", "set_precision", "get_precision", "set_backward_check", "get_backward_check", "HintFlow", "GraphedFlow", "nll_loss",
            "BucketedGradAllReduce", "broadcast_parameters", "shard_rows",
-           "FusedClampAdam", "FusedTrainStep", "add_noise", "nll_loss_fused"]
+           "FusedClampAdam", "FusedTrainStep", "add_noise", "nll_loss_fused", "multi_mmd"]

@@ -23,6 +23,7 @@ EXPORTS = [
     "hint_householder_matrix", "hint_householder_matrix_backward", "hint_householder_apply",
     "hint_householder_wgrad_workspace_bytes", "hint_householder_wgrad",
     "hint_mlp_coupling_supported", "hint_mlp_coupling_forward", "hint_mlp_coupling_workspace_bytes", "hint_mlp_coupling_backward",
+    "hint_mmd_workspace_bytes", "hint_multi_mmd",
 ]
 
 
@@ -119,6 +120,10 @@ def load():
     lib.hint_mlp_coupling_backward.restype = ctypes.c_int
     lib.hint_mlp_coupling_backward.argtypes = [f32p, i32, f32p, i32, i32, ctypes.POINTER(vp), f32, i64, f32p, f32p, f32p, f32p, ctypes.POINTER(vp),
                                                vp, ctypes.c_size_t, vp]
+    lib.hint_mmd_workspace_bytes.restype = ctypes.c_size_t
+    lib.hint_mmd_workspace_bytes.argtypes = [i64]
+    lib.hint_multi_mmd.restype = ctypes.c_int
+    lib.hint_multi_mmd.argtypes = [f32p, f32p, i64, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), i32, f32p, vp, ctypes.c_size_t, vp]
     lib.hint_launch_count.restype = ctypes.c_uint64
     lib.hint_launch_count.argtypes = []
     lib.hint_last_error.restype = ctypes.c_char_p

@@ -28,7 +28,8 @@ UNITS = {
     "train_ops.cu": ["train_ops.h", "launch_count.h", HDR_API],
     "householder.cu": ["householder.h", "launch_count.h", HDR_API],
     "mlp_coupling.cu": ["mlp_coupling.h", "launch_count.h", HDR_API],
-    "capi.cu": ["train_ops.h", "householder.h", "mlp_coupling.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 
+    "mmd.cu": ["mmd.h", "launch_count.h", HDR_API],
+    "capi.cu": ["train_ops.h", "householder.h", "mlp_coupling.h", "mmd.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 
                 "simt_phases.cuh", "simt_kernels.cuh", HDR_API],
 }
 NVCC_FLAGS = ["-O3", "-std=c++17", "-DHINT_MMA_MINB=2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -21,6 +21,7 @@
 #include "train_ops.h"
 #include "householder.h"
 #include "mlp_coupling.h"
+#include "mmd.h"
 #include "simt_kernels.cuh"
 
 using namespace hint;
@@ -630,6 +631,19 @@ int hint_mlp_coupling_backward(const float* u, int32_t du, const float* v, int32
     if (!workspace || workspace_bytes < mc_workspace_bytes(du, dv, hidden, (long long)B)) return fail(HINT_ERR_WORKSPACE, "workspace too small");
     CUDA_TRY(mc_backward(u, du, v, dv, hidden, params, clamp, (long long)B, dy, dlogdet, du_grad, dv_grad, dparams, workspace, workspace_bytes,
                          (cudaStream_t)stream));
+    return HINT_OK;
+}
+
+size_t hint_mmd_workspace_bytes(int64_t n) { return n >= 1 ? mmd_workspace_bytes((long long)n) : 0; }
+
+int hint_multi_mmd(const float* x, const float* y, int64_t n, int32_t d, const float* widths, const float* exponents, int32_t n_kernels,
+                   float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 1 || d < 1 || !x || !y || !out || !widths || !exponents || n_kernels < 1 || n_kernels > 8)
+        return fail(HINT_ERR_INVALID, "bad MMD arguments (n >= 1, d >= 1, 1 <= n_kernels <= 8)");
+    for (int i = 0; i < n_kernels; ++i)
+        if (!(widths[i] > 0.f) || !(exponents[i] > 0.f)) return fail(HINT_ERR_INVALID, "MMD kernel widths and exponents must be positive");
+    if (!workspace || workspace_bytes < mmd_workspace_bytes((long long)n)) return fail(HINT_ERR_WORKSPACE, "workspace too small");
+    CUDA_TRY(mmd_multi(x, y, (long long)n, d, widths, exponents, n_kernels, out, workspace, workspace_bytes, (cudaStream_t)stream));
     return HINT_OK;
 }
 

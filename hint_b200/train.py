@@ -161,3 +161,25 @@ class FusedTrainStep:
             hd.wait()
         self.opt.step()
         return loss
+
+
+def multi_mmd(x, y, widths_exponents=((0.5, 1), (0.2, 1), (0.2, 0.5))):
+    """The sampling scripts' evaluation metric (rejection_sampling.py:56-73): multi-kernel MMD^2 of two sets of n samples with
+    inverse-multiquadric kernels, as ONE fused pair-tile kernel (nothing n x n is materialised) -> 0-dim device tensor.  No autograd
+    (the reference only evaluates it)."""
+    if not (x.is_cuda and y.is_cuda) or x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise RuntimeError("hint_b200.multi_mmd: float32 CUDA tensors required (there is no CPU path)")
+    if x.dim() != 2 or x.shape != y.shape:
+        raise ValueError("hint_b200.multi_mmd: x and y must both be [n, d] (the reference averages XX + YY - 2 XY elementwise)")
+    x, y = x.detach().contiguous(), y.detach().contiguous()
+    n, d = x.shape
+    k = len(widths_exponents)
+    C = (ctypes.c_float * k)(*[float(w) for w, _ in widths_exponents])
+    a = (ctypes.c_float * k)(*[float(e) for _, e in widths_exponents])
+    lib = _lib.load()
+    with _lib.on_device(x.device):
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        nbytes = lib.hint_mmd_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.hint_multi_mmd(x.data_ptr(), y.data_ptr(), n, d, C, a, k, out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    return out

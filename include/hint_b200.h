@@ -175,6 +175,15 @@ int hint_mlp_coupling_backward(const float* u, int32_t du, const float* v, int32
                                float clamp, int64_t B, const float* dy, const float* dlogdet, float* du_grad, float* dv_grad,
                                float* const* dparams, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- evaluation metric of the sampling scripts (rejection_sampling.py:56-73 `multi_mmd`) ---------------------
+ *     out[0] = mean_ij [ k(|x_i - x_j|^2) + k(|y_i - y_j|^2) - 2 k(|x_i - y_j|^2) ],  k(D) = sum_w C_w^a_w ((C_w + D) / a_w)^(-a_w)
+ * x, y [n,d] device, widths C_w / exponents a_w: HOST arrays of n_kernels <= 8 positive values (the script's default:
+ * {0.5, 0.2, 0.2} / {1, 1, 0.5}); out: one device float.  One fused pair-tile kernel + a fixed-order fp64 reduction
+ * (deterministic); nothing of size n x n is materialised. */
+size_t hint_mmd_workspace_bytes(int64_t n);
+int hint_multi_mmd(const float* x, const float* y, int64_t n, int32_t d, const float* widths, const float* exponents, int32_t n_kernels,
+                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 const char* hint_last_error(void);
 /* "hint_b200 <version> sm_100a" — lets the host check it loaded the in-tree build */
 const char* hint_version(void);

@@ -293,3 +293,30 @@ def test_graphed_flow_replays_the_same_transport(dev):
                 gf(torch.randn(B + 1, d, device=dev))
     finally:
         hint_b200.set_precision(old)
+
+
+@pytest.mark.parametrize("n,d", [(4000, 20), (1000, 100), (65, 3), (1, 4), (333, 33)])
+def test_fused_multi_mmd_matches_the_scripts_estimator(dev, n, d):
+    """hint_multi_mmd against rejection_sampling.py:56-73 restated in float64 (same kernels, same mean over the n x n matrix)."""
+    import hint_b200
+    g = torch.Generator().manual_seed(n + d)
+    x = torch.randn(n, d, generator=g)
+    y = 0.3 + 1.2 * torch.randn(n, d, generator=g)
+    we = [(0.5, 1), (0.2, 1), (0.2, 0.5)]
+
+    def ref(a, b, we):
+        d2 = lambda p, q: torch.cdist(p.double(), q.double()).pow(2)
+        k = lambda dd: sum(C ** e * ((C + dd) / e) ** -e for C, e in we)
+        return float((k(d2(a, a)) + k(d2(b, b)) - 2 * k(d2(a, b))).mean())
+    n0 = hint_b200._lib.load().hint_launch_count()
+    got = float(hint_b200.multi_mmd(x.to(dev), y.to(dev), we))
+    assert hint_b200._lib.load().hint_launch_count() == n0 + 2
+    want = ref(x, y, we)
+    assert abs(got - want) <= 2e-5 * max(1e-2, abs(want)), (got, want)
+    # identical sets: exactly the estimator's zero (up to fp32 rounding of the kernel values)
+    assert abs(float(hint_b200.multi_mmd(x.to(dev), x.to(dev), we))) < 1e-6
+    # generic exponents go through powf
+    we2 = [(1, 0.5), (0.2, 0.8), (0.2, 0.4)]
+    got2, want2 = float(hint_b200.multi_mmd(x.to(dev), y.to(dev), we2)), ref(x, y, we2)
+    assert abs(got2 - want2) <= 5e-5 * max(1e-2, abs(want2)), (got2, want2)
+    assert float(hint_b200.multi_mmd(x.to(dev), y.to(dev), we)) == got       # deterministic
