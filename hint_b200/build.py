@@ -26,7 +26,7 @@ UNITS = {
     "chain_launch.cu": ["launch_count.h", "plan.h", "plan_mma.h", "plan_chain.h", "chain_launch.h", "mma_kernels.cuh", "chain_kernels.cuh", HDR_API],
     "mma_launch.cu": ["launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "mma_kernels.cuh", HDR_API],
     "train_ops.cu": ["train_ops.h", "launch_count.h", HDR_API],
-    "householder.cu": ["householder.h", "launch_count.h", HDR_API],
+    "householder.cu": ["householder.h", "mlp_coupling.h", "launch_count.h", HDR_API],
     "mlp_coupling.cu": ["mlp_coupling.h", "launch_count.h", HDR_API],
     "mmd.cu": ["mmd.h", "launch_count.h", HDR_API],
     "capi.cu": ["train_ops.h", "householder.h", "mlp_coupling.h", "mmd.h", "launch_count.h", "plan.h", "plan_mma.h", "mma_launch.h", "plan_chain.h", "chain_launch.h", "plan_tc3.h", "tc3_launch.h", "tcgen05.cuh", 

@@ -56,12 +56,7 @@ def backward(u, v, params, clamp, dy, djac):
     lib = _lib.load()
     with _lib.on_device(u.device):
         gu, gv = torch.empty_like(u), torch.empty_like(v)
-        sizes = [p.numel() for p in params]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=u.device)    # one allocation for the 16 parameter gradients
-        gp, off = [], 0
-        for p, n in zip(params, sizes):
-            gp.append(flat[off:off + n].view(p.shape))
-            off += n
+        gp = [torch.empty_like(p) for p in params]     # (16 cached-allocator hits: cheaper on the host than views of one buffer)
         nbytes = lib.hint_mlp_coupling_workspace_bytes(du, dv, H, B)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=u.device)
         _lib.check(lib.hint_mlp_coupling_backward(u.data_ptr(), du, v.data_ptr(), dv, H, _ptrs(params), float(clamp), B, dy.data_ptr(),

@@ -10,12 +10,13 @@
 //                              dv = -2/s (b + e) + 4 (c . a) / s^2 v,   s = |v|^2,  W' = W_{k-1}
 //   hh_apply_kernel        y = x W or x W^T: error-compensated 3 x TF32 warp MMAs (fp32-grade: the mixing must stay orthogonal to
 //                          1e-6), W resident in shared memory, per-warp cp.async double-buffered row ranges
-//   hh_wgrad_kernel        dW = x^T dz: per-CTA partials in registers over its row tiles, fixed-order second stage (deterministic)
+//   hh_wgrad               dW = x^T dz on the couplings' weight-gradient kernel (mlp_coupling.cu: 3 x TF32 MMAs, deterministic)
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
 #include "householder.h"
+#include "mlp_coupling.h"
 #include "launch_count.h"
 
 namespace hint {
@@ -255,69 +256,6 @@ __global__ void __launch_bounds__(kHhApplyThreads) hh_apply_kernel(const float* 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// partial[cta][i][j] = sum over the CTA's rows of x[r][i] dz[r][j];  thread (ig = tid / 16, jg = tid % 16) owns the 4 x 4 blocks
-// (ig + 16 a, jg + 16 b), a, b < 2  -> d <= 128.
-__global__ void __launch_bounds__(kHhThreads) hh_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, long long B, int d,
-                                                              float* __restrict__ partial) {
-    extern __shared__ __align__(16) float sm[];
-    const int dp = ((d + 3) & ~3) + 4;           // row pitch in floats (16-byte aligned rows, padded)
-    constexpr int TR = 32;                        // rows per step
-    float* Xs = sm;                               // [TR][dp]
-    float* Zs = Xs + TR * dp;                     // [TR][dp]
-    const int ig = threadIdx.x >> 4, jg = threadIdx.x & 15;
-    float acc[2][2][4][4] = {};
-    const long long nsteps = (B + TR - 1) / TR;
-    for (long long st = blockIdx.x; st < nsteps; st += gridDim.x) {
-        const long long row0 = st * TR;
-        const int rows = (int)((B - row0) < TR ? (B - row0) : TR);
-        __syncthreads();
-        for (int i = threadIdx.x; i < TR * dp; i += kHhThreads) {
-            const int r = i / dp, k = i - r * dp;
-            const bool ok = r < rows && k < d;
-            Xs[i] = ok ? __ldg(x + (row0 + r) * d + k) : 0.f;
-            Zs[i] = ok ? __ldg(dz + (row0 + r) * d + k) : 0.f;
-        }
-        __syncthreads();
-        for (int r = 0; r < TR; ++r) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int i0 = 4 * (ig + 16 * a);
-                if (i0 >= d) continue;
-                const float4 xv = *reinterpret_cast<const float4*>(Xs + r * dp + i0);
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int j0 = 4 * (jg + 16 * b);
-                    if (j0 >= d) continue;
-                    const float4 zv = *reinterpret_cast<const float4*>(Zs + r * dp + j0);
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-                    for (int p = 0; p < 4; ++p)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[a][b][p][q] = fmaf(xs[p], zs[q], acc[a][b][p][q]);
-                }
-            }
-        }
-    }
-    float* out = partial + (size_t)blockIdx.x * d * d;
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = 4 * (ig + 16 * a) + p, j = 4 * (jg + 16 * b) + q;
-                    if (i < d && j < d) out[i * d + j] = acc[a][b][p][q];
-                }
-}
-__global__ void hh_wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int n, float* __restrict__ dW) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float a = 0.f;
-        for (int q = 0; q < nctas; ++q) a += partial[(size_t)q * n + i];
-        dW[i] = a;
-    }
-}
 
 int hh_sms() {
     int dev = 0, sms = 148;
@@ -369,22 +307,13 @@ cudaError_t hh_apply(const float* x, const float* W, long long B, int d, int tra
     return d <= 48 ? hh_apply_launch<2, 6>(x, W, B, d, transpose, y, st) : hh_apply_launch<1, 16>(x, W, B, d, transpose, y, st);
 }
 
-size_t hh_wgrad_workspace_bytes(int d) { return sizeof(float) * (size_t)hh_sms() * 2 * d * d; }
+size_t hh_wgrad_workspace_bytes(int d) { return mc_xt_y_workspace_bytes(d, d); }
 
+// dW = x^T dz on the couplings' weight-gradient kernel (3 x TF32 MMAs, the samples split over warps and CTAs, fixed-order
+// reductions): d = 43, 2^20 rows 1.16 ms (FFMA register-tile version) -> see profiles/ncu_r02_hh_apply.txt
 cudaError_t hh_wgrad(const float* x, const float* dz, long long B, int d, float* dW, void* workspace, cudaStream_t st) {
     if (d < 1 || d > kHhMaxD || B < 0) return cudaErrorInvalidValue;
-    const int dp = ((d + 3) & ~3) + 4;
-    const size_t smem = sizeof(float) * 2 * 32 * dp;
-    const long long nsteps = (B + 31) / 32;
-    int grid = (int)(nsteps < (long long)hh_sms() * 2 ? nsteps : (long long)hh_sms() * 2);
-    if (grid < 1) grid = 1;
-    float* partial = reinterpret_cast<float*>(workspace);
-    hh_wgrad_kernel<<<grid, kHhThreads, smem, st>>>(x, dz, B, d, partial); HINT_LAUNCHED();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const int n = d * d;
-    hh_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, grid, n, dW); HINT_LAUNCHED();
-    return cudaGetLastError();
+    return mc_xt_y(x, dz, d, d, B, dW, workspace, hh_wgrad_workspace_bytes(d), st);
 }
 
 }  // namespace hint

@@ -442,6 +442,15 @@ cudaError_t mc_geometry(const void* fn, int floats, int H, long long B, int* nw,
 }
 
 constexpr int kMcMaxSplit = 32;
+// CTAs of the weight-gradient kernel that are resident at once on the device: the sample splits fill exactly one wave
+int mc_wgrad_resident() {
+    static const int n = [] {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)mc_wgrad_kernel, 32 * kMcWgWarps, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        return per_sm * mc_sms();
+    }();
+    return n;
+}
 size_t mc_param_floats(int du, int dv, int H) { return 2 * ((size_t)H * du + 2 * (size_t)H * H + (size_t)dv * H + 3 * (size_t)H + dv); }
 
 }  // namespace
@@ -514,8 +523,8 @@ cudaError_t mc_backward(const float* u, int du, const float* v, int dv, int H, c
             blocks += ((p.N + 15) / 16) * p.tiles_k;
         }
     }
-    // enough blocks for two per SM: split the samples when the output tiles alone are too few (each split >= 64 samples)
-    long long nsplit = (2LL * mc_sms() + blocks - 1) / blocks;
+    // one full wave of CTAs: split the samples when the output tiles alone are too few (each split >= 64 samples)
+    long long nsplit = mc_wgrad_resident() / blocks;
     const long long by_rows = (B + 63) / 64;
     nsplit = nsplit > by_rows ? by_rows : nsplit;
     nsplit = nsplit > kMcMaxSplit ? kMcMaxSplit : nsplit < 1 ? 1 : nsplit;
@@ -523,6 +532,36 @@ cudaError_t mc_backward(const float* u, int du, const float* v, int dv, int H, c
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nsplit > 1) {
         mc_wgrad_reduce_kernel<<<dim3(32, 8), 256, 0, st>>>(wg, (int)nsplit); HINT_LAUNCHED();
+    }
+    return cudaGetLastError();
+}
+
+// out[N][K] = Dm^T X for Dm [B][N], X [B][K] with the weight-gradient kernel above (one problem, more sample splits): used by the
+// Householder mixing's dW = x^T dy.  Workspace: N floats (unused bias sums) + splits x (N K + N) partials.
+constexpr int kMcXtySplit = 128;
+size_t mc_xt_y_workspace_bytes(int N, int K) { return sizeof(float) * ((size_t)N + (size_t)kMcXtySplit * ((size_t)N * K + N)) + 64; }
+
+cudaError_t mc_xt_y(const float* Dm, const float* X, int N, int K, long long B, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (N < 1 || K < 1 || B < 0 || ws_bytes < mc_xt_y_workspace_bytes(N, K)) return cudaErrorInvalidValue;
+    if (B == 0) return cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * K, st);
+    McWgArgs wg;
+    wg.B = B;
+    float* f = static_cast<float*>(ws);
+    wg.partial = f + N;
+    wg.pstride = (long long)N * K + N;
+    for (int i = 0; i < 8; ++i) { wg.p[i] = McWgProb{}; wg.p[i].first_block = 0x7fffffff; }
+    McWgProb& p = wg.p[0];
+    p.Dm = Dm; p.X = X; p.dW = out; p.db = f; p.N = N; p.K = K; p.tiles_k = (K + 31) / 32; p.first_block = 0; p.poff = 0;
+    const int blocks = ((N + 15) / 16) * p.tiles_k;
+    long long nsplit = mc_wgrad_resident() / blocks;
+    const long long by_rows = (B + 255) / 256;
+    nsplit = nsplit > by_rows ? by_rows : nsplit;
+    nsplit = nsplit > kMcXtySplit ? kMcXtySplit : nsplit < 1 ? 1 : nsplit;
+    mc_wgrad_kernel<<<dim3(blocks, (unsigned)nsplit), 32 * kMcWgWarps, 0, st>>>(wg); HINT_LAUNCHED();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (nsplit > 1) {
+        mc_wgrad_reduce_kernel<<<dim3(32, 1), 256, 0, st>>>(wg, (int)nsplit); HINT_LAUNCHED();
     }
     return cudaGetLastError();
 }

@@ -16,4 +16,8 @@ cudaError_t mc_backward(const float* u, int du, const float* v, int dv, int H, c
                         const float* dy, const float* dlogdet, float* du_grad, float* dv_grad, float* const* dparams, void* ws,
                         size_t ws_bytes, cudaStream_t st);
 
+// out[N][K] = Dm^T X (Dm [B][N], X [B][K]), fp32-grade, deterministic
+size_t mc_xt_y_workspace_bytes(int N, int K);
+cudaError_t mc_xt_y(const float* Dm, const float* X, int N, int K, long long B, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace hint
