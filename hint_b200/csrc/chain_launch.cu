@@ -53,6 +53,8 @@ FwdCfg pick_fwd(const Plan& p, const ChainPlan& c) {
         f.smem = fwd_smem(p, c, f.mt, f.nw, f.ws);
         return f;
     }
+    // 32 samples per warp (MT = 2: half the B-fragment loads per sample, 218 registers, 8 warps) was measured too: 1.21 ms forward /
+    // 0.89 ms inverse against 0.95 / 0.89 ms for MT = 1 with 12 warps - fewer warps lose more than the operand reuse gains
     for (int nw : {12, 8}) {      // measured (d=43): 8 warps 1.52 ms, 12 warps 0.96 ms, 14 warps 1.00 ms - beyond 12 the shared-memory
                                   // pipe (one 256-byte B fragment per MMA at 16 samples per warp) is saturated
         const size_t b = fwd_smem(p, c, 1, nw, 1);
