@@ -125,3 +125,69 @@ def test_paths_the_kernels_do_not_cover_fall_back_to_pytorch(dev):
     md.eval()
     md([x.detach()])
     assert hint_b200._lib.load().hint_launch_count() == n0 + 1
+
+
+def test_two_lane_conditional_model_trains_like_the_pytorch_couplings(dev, monkeypatch):
+    """The lens `conditional_hint_*_full` architecture (configs/lens_shape/conditional_hint_8_full.py:61-102, two blocks here)
+    through the FrEIA shim, driven like train_conditional.py:119-156 (NLL of both lanes, Adam): the run with the fused coupling
+    kernels follows the run with the plain-PyTorch couplings (same seed, fp32 HINT kernels) step for step."""
+    import hint_b200
+    from FrEIA.framework import InputNode, Node, OutputNode, ReversibleGraphNet
+    from FrEIA.modules import (HierarchicalAffineCouplingBlock, HouseholderPerm, AffineCoupling, ExternalAffineCoupling,
+                               F_fully_connected)
+    from FrEIA.modules import coupling as shim
+
+    def build():
+        torch.manual_seed(0)
+        y_lane, x_lane = [InputNode(2, name="y")], [InputNode(20, name="x")]
+        for i in range(2):
+            if i > 0:
+                y_lane.append(Node(y_lane[-1], HouseholderPerm, {"fixed": True, "n_reflections": 2}, name=f"perm_y_{i}"))
+                x_lane.append(Node(x_lane[-1], HouseholderPerm, {"fixed": True, "n_reflections": 20}, name=f"perm_x_{i}"))
+            x_lane.append(Node(x_lane[-1], HierarchicalAffineCouplingBlock, {"c_internal": [68, 34, 17, 17]}, name=f"hac_x_{i+1}"))
+            x_lane.append(Node(x_lane[-1], ExternalAffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": 68}},
+                               conditions=y_lane[-1], name=f"ac_y_to_x_{i+1}"))
+            y_lane.append(Node(y_lane[-1], AffineCoupling, {"F_class": F_fully_connected, "F_args": {"internal_size": 17}}, name=f"ac_y_{i+1}"))
+        y_lane.append(OutputNode(y_lane[-1], name="z_y"))
+        x_lane.append(OutputNode(x_lane[-1], name="z_x"))
+        m = ReversibleGraphNet(y_lane + x_lane, verbose=False)
+        for p in m.parameters():
+            if p.requires_grad:
+                p.data = 0.05 * torch.randn_like(p)
+        return m.to(dev)
+
+    def run(m):
+        g = torch.Generator().manual_seed(3)
+        x = (1.0 + 2.0 * torch.randn(2000, 20, generator=g)).to(dev)
+        y = torch.randn(2000, 2, generator=g).to(dev)
+        opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+        losses = []
+        for _ in range(4):
+            opt.zero_grad()
+            z_y, z_x = m([y, x])
+            J = m.log_jacobian(run_forward=False)
+            loss = 0.5 * (z_y.pow(2).sum(1) + z_x.pow(2).sum(1)).mean() - J.mean()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        with torch.no_grad():
+            y2, x2 = m(list(m([y, x])), rev=True)
+        return losses, float((x2 - x).abs().max()), float((y2 - y).abs().max())
+
+    old = hint_b200.get_precision()
+    hint_b200.set_precision("fp32")
+    try:
+        n0 = hint_b200._lib.load().hint_launch_count()
+        fused, ex, ey = run(build())
+        n_fused = hint_b200._lib.load().hint_launch_count() - n0
+        monkeypatch.setattr(shim._AffineBase, "_fused", lambda self, u, v, rev: None)
+        n0 = hint_b200._lib.load().hint_launch_count()
+        plain, _, _ = run(build())
+        n_plain = hint_b200._lib.load().hint_launch_count() - n0
+    finally:
+        hint_b200.set_precision(old)
+    assert n_fused > n_plain                       # the couplings really ran on the library's kernels
+    assert fused[-1] < fused[0]
+    for a, b in zip(fused, plain):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (fused, plain)
+    assert ex < 1e-3 and ey < 1e-4
