@@ -143,3 +143,33 @@ def test_reshuffle_composes_into_one_matrix_in_front_of_the_tree(name):
     xi, Ji = O.forward(plan, f64, x, c, rev=True, clamp=pk["clamp"])
     assert float((xi @ M.t() - torch.from_numpy(g["xinv64"])).abs().max()) < 1e-12
     assert float((Ji - torch.from_numpy(g["Jinv64"])).abs().max()) < 1e-12
+
+
+def test_widening_entry_points_validate_their_arguments_without_a_gpu():
+    """Argument checks of the training-edge / Householder / coupling / MMD entry points return the documented status codes before
+    any CUDA call (no device needed), and the size queries answer on the host."""
+    import ctypes
+    lib = _lib.load()
+    vp16 = (ctypes.c_void_p * 16)()
+    one = ctypes.c_void_p(16)      # a non-null placeholder pointer: rejected calls never dereference it
+    assert lib.hint_mlp_coupling_supported(2, 20, 68) == 1
+    assert lib.hint_mlp_coupling_supported(0, 20, 68) == 0 and lib.hint_mlp_coupling_supported(2, 129, 68) == 0
+    assert lib.hint_mlp_coupling_supported(2, 20, 257) == 0
+    assert lib.hint_mlp_coupling_forward(one, 2, one, 200, 68, vp16, 5.0, 0, 10, one, one, None) == _lib.HINT_ERR_UNSUPPORTED
+    assert lib.hint_mlp_coupling_forward(one, 2, one, 20, 68, vp16, 5.0, 0, 10, one, one, None) == _lib.HINT_ERR_INVALID   # null parameters
+    assert "null parameter" in _lib.last_error()
+    assert lib.hint_mlp_coupling_forward(one, 2, one, 20, 68, vp16, 5.0, 0, -1, one, one, None) == _lib.HINT_ERR_INVALID
+    assert lib.hint_mlp_coupling_workspace_bytes(2, 20, 68, 1000) >= 4 * 2 * 1000 * (6 * 68 + 20)
+    assert lib.hint_mlp_coupling_workspace_bytes(2, 200, 68, 1000) == 0
+    full16 = (ctypes.c_void_p * 16)(*[16] * 16)
+    assert lib.hint_mlp_coupling_backward(one, 2, one, 20, 68, full16, 5.0, 10, one, None, one, one, full16, one, 8, None) == _lib.HINT_ERR_WORKSPACE
+    f3 = (ctypes.c_float * 3)(0.5, 0.2, 0.2)
+    bad = (ctypes.c_float * 3)(0.5, -0.2, 0.2)
+    assert lib.hint_mmd_workspace_bytes(4000) >= 8 * 3 * 63 * 63
+    assert lib.hint_multi_mmd(one, one, 0, 20, f3, f3, 3, one, one, 1 << 20, None) == _lib.HINT_ERR_INVALID
+    assert lib.hint_multi_mmd(one, one, 100, 20, f3, bad, 3, one, one, 1 << 20, None) == _lib.HINT_ERR_INVALID
+    assert lib.hint_multi_mmd(one, one, 100, 20, f3, f3, 9, one, one, 1 << 20, None) == _lib.HINT_ERR_INVALID
+    assert lib.hint_multi_mmd(one, one, 4000, 20, f3, f3, 3, one, one, 8, None) == _lib.HINT_ERR_WORKSPACE
+    assert lib.hint_householder_apply(one, one, 10, 129, 0, one, None) == _lib.HINT_ERR_INVALID
+    assert lib.hint_householder_apply(one, one, 10, 20, 0, one, None) == _lib.HINT_ERR_INVALID        # y aliases x
+    assert lib.hint_householder_wgrad_workspace_bytes(43) > 0 and lib.hint_householder_wgrad_workspace_bytes(0) == 0
