@@ -174,8 +174,10 @@ struct McFwdArgs {
     long long B; int du, dv, H; float alpha; int rev;
 };
 
-// One CTA = one tile of 16 samples at a time; its warps split every layer's output columns.
-__global__ void __launch_bounds__(kMcThreads) mc_forward_kernel(McFwdArgs a) {
+// One CTA = one tile of 16 samples at a time; its warps split every layer's output columns.  (At most 8 warps are launched; the
+// register cap of 3 CTAs x 256 threads leaves the forward at 76 registers without spills and five CTAs of 5 warps per SM for the
+// lens shape: hidden = 224 forward 330 -> 265 us.  The backward kernel spills under the same cap and is slower: left alone.)
+__global__ void __launch_bounds__(256, 3) mc_forward_kernel(McFwdArgs a) {
     extern __shared__ __align__(16) float sm[];
     const McDims D(a.du, a.dv, a.H);
     const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
