@@ -250,7 +250,7 @@ struct McBwdArgs {
 __host__ __device__ inline size_t mc_net_floats(long long B, int dv, int H) { return (size_t)B * (6 * (size_t)H + dv); }
 
 // rev = 0 direction only (the training direction, train_conditional.py:119-156)
-__global__ void __launch_bounds__(kMcThreads) mc_backward_kernel(McBwdArgs a) {
+__global__ void __launch_bounds__(320, 2) mc_backward_kernel(McBwdArgs a) {
     extern __shared__ __align__(16) float sm[];
     const McDims D(a.du, a.dv, a.H);
     float* U = sm;
