@@ -320,3 +320,43 @@ def test_fused_multi_mmd_matches_the_scripts_estimator(dev, n, d):
     got2, want2 = float(hint_b200.multi_mmd(x.to(dev), y.to(dev), we2)), ref(x, y, we2)
     assert abs(got2 - want2) <= 5e-5 * max(1e-2, abs(want2)), (got2, want2)
     assert float(hint_b200.multi_mmd(x.to(dev), y.to(dev), we)) == got       # deterministic
+
+
+def test_householder_mixing_at_the_benchmark_size_preserves_norms_and_inverts(dev):
+    """Size-independent properties at BASELINE's full batch (2^20 rows, d = 43): the mixing is an isometry (row norms kept to
+    fp32 rounding), x W W^T = x, and it is linear ((x + y) W = x W + y W)."""
+    from hint_b200.householder import householder_matrix, householder_apply
+    torch.manual_seed(0)
+    B, d = 1 << 20, 43
+    W = householder_matrix(torch.randn(d, d, device=dev))
+    x = torch.randn(B, d, device=dev)
+    y = householder_apply(x, W)
+    nx, ny = x.double().norm(dim=1), y.double().norm(dim=1)
+    assert float(((ny - nx).abs() / nx).max()) < 5e-6
+    back = householder_apply(y, W, transpose=True)
+    assert float((back - x).abs().max()) < 2e-5
+    x2 = torch.randn(B, d, device=dev)
+    lin = householder_apply(x + x2, W) - y - householder_apply(x2, W)
+    assert float(lin.abs().max()) < 2e-5
+
+
+def test_fused_coupling_round_trip_at_a_large_batch(dev):
+    """2^20 samples through the lens y -> x coupling and back: the inverse undoes the forward pass, the log-dets cancel, and the
+    rows are independent (a permuted batch gives the permuted result bit for bit)."""
+    from FrEIA.modules import ExternalAffineCoupling, F_fully_connected
+    torch.manual_seed(1)
+    m = ExternalAffineCoupling([(20,)], dims_c=[(2,)], F_class=F_fully_connected, F_args={"internal_size": 68}).to(dev)
+    for p in m.parameters():
+        p.data = 0.05 * torch.randn_like(p)
+    B = 1 << 20
+    x, c = torch.randn(B, 20, device=dev), torch.randn(B, 2, device=dev)
+    with torch.no_grad():
+        y = m([x], [c])[0]
+        j = m.jacobian(None)
+        back = m([y], [c], rev=True)[0]
+        jb = m.jacobian(None)
+        perm = torch.randperm(B, device=dev)
+        yp = m([x[perm]], [c[perm]])[0]
+    assert float((back - x).abs().max()) < 1e-4
+    assert float((j + jb).abs().max()) < 1e-5
+    assert torch.equal(yp, y[perm])
