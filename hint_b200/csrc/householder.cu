@@ -13,6 +13,7 @@
 //   hh_wgrad               dW = x^T dz on the couplings' weight-gradient kernel (mlp_coupling.cu: 3 x TF32 MMAs, deterministic)
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 
 #include "householder.h"
@@ -289,12 +290,17 @@ cudaError_t hh_apply_launch(const float* x, const float* W, long long B, int d, 
     nw = nw > kHhApplyThreads / 32 ? kHhApplyThreads / 32 : nw < 1 ? 1 : nw;
     const size_t smem = wbytes + nw * per_warp;
     const void* fn = (const void*)hh_apply_kernel<MT, NTC>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * nw, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    // CTAs per SM for this d: asked once (the attribute call + occupancy query cost ~10 us of host time per launch otherwise)
+    static std::atomic<int> cached[kHhMaxD + 1];
+    int per_sm = cached[d].load(std::memory_order_relaxed);
+    if (per_sm < 1) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * nw, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        cached[d].store(per_sm, std::memory_order_relaxed);
+    }
     const long long nranges = (B + RW - 1) / RW, want = (nranges + nw - 1) / nw, cap = (long long)hh_sms() * per_sm;
     hh_apply_kernel<MT, NTC><<<(int)(want < cap ? want : cap), 32 * nw, smem, st>>>(x, W, B, d, transpose, y); HINT_LAUNCHED();
     return cudaGetLastError();

@@ -19,6 +19,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "launch_count.h"
 #include "mlp_coupling.h"
@@ -426,18 +429,33 @@ void mc_fill(McNet (&net)[2], const float* const* params) {
         for (int l = 0; l < 4; ++l) { net[n].W[l] = params[8 * n + 2 * l]; net[n].b[l] = params[8 * n + 2 * l + 1]; }
 }
 
+// CTAs per SM of (kernel, block size, dynamic shared memory): the attribute call and the occupancy query cost ~10 us of host time,
+// which matters for kernels that run for 20 us - asked once per distinct configuration
+cudaError_t mc_occupancy(const void* fn, int threads, size_t smem, int* per_sm) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, size_t>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(fn, threads, smem);
+    const auto it = cache.find(key);
+    if (it != cache.end()) { *per_sm = it->second; return cudaSuccess; }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (*per_sm < 1) return cudaErrorInvalidConfiguration;
+    cache[key] = *per_sm;
+    return cudaSuccess;
+}
+
 // warps per CTA (they split a layer's n-tile pairs) and the grid (one 16-sample tile per CTA at a time)
 cudaError_t mc_geometry(const void* fn, int floats, int H, long long B, int* nw, size_t* smem, int* grid) {
     const int pairs = (((H + 7) >> 3) + kMcNc - 1) / kMcNc;
     *nw = pairs < 1 ? 1 : pairs > 8 ? 8 : pairs;
     *smem = sizeof(float) * (size_t)floats;
     if (*smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * *nw, *smem);
+    cudaError_t e = mc_occupancy(fn, 32 * *nw, *smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const long long ntiles = (B + 15) / 16, cap = (long long)mc_sms() * per_sm;
     *grid = (int)(ntiles < cap ? ntiles : cap);
     return cudaSuccess;
